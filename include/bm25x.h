@@ -1,0 +1,141 @@
+/*
+ * bm25x.h — C ABI of the B200-native BM25 top-k engine (libbm25x.so).
+ *
+ * This is the drop-in boundary for ONE path of tensorchord/VectorChord-bm25: the
+ * ranked top-k query `bm25::search` (and, next, `bm25::evaluate`).  Each entry
+ * point cites the reference interface it replaces (paths relative to the
+ * reference tree).  Plain pointers and sizes only: no C++/torch types, no
+ * exceptions or unwinding across the boundary (the reference denies
+ * ffi_unwind_calls, src/lib.rs:16): every call returns an int status and
+ * bm25x_last_error() holds a thread-local message.
+ *
+ * There is NO CPU fallback: every search entry point fails with
+ * BM25X_ERR_CUDA when no sm_100 device / kernel image is available.
+ */
+#ifndef BM25X_H
+#define BM25X_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BM25X_OK 0
+#define BM25X_ERR_INVALID 1     /* bad argument / corrupt corpus ("data corruption" panics in the reference) */
+#define BM25X_ERR_CUDA 2        /* CUDA runtime / launch failure, or no usable device */
+#define BM25X_ERR_OOM 3
+#define BM25X_ERR_UNSUPPORTED 4 /* k > BM25X_MAX_K, > BM25X_MAX_QUERY_TERMS live terms, tf >= 2^24 */
+#define BM25X_ERR_LIMIT_ZERO 5  /* k == 0: "number of needed rows is set to 0" (scanners/default.rs:114-116) */
+
+#define BM25X_MAX_K 1024
+#define BM25X_MAX_QUERY_TERMS 32
+#define BM25X_TERM_MISSING 0xFFFFFFFFu
+#define BM25X_KEY_WIDTH 16 /* crates/bm25/src/lib.rs:37 WIDTH */
+
+typedef struct bm25x_index bm25x_index;
+typedef struct bm25x_batch bm25x_batch;
+
+/* The sealed segment as the reference hands it to flush():
+ * `Segment{records: Record(len, payload), mappings: Mapping(key, doc, tf)}` sorted by (key, doc)
+ * (crates/bm25/src/segment.rs:19-45, flush.rs:40-67).  Term-major CSR on the host. */
+typedef struct {
+    uint32_t n_docs;          /* number_of_documents; doc id = record order (io.rs:52-60) */
+    const uint32_t *doc_len;  /* [n_docs] exact document length = Σ tf (vector.rs:77-83) */
+    const uint16_t *payload;  /* [n_docs*3] heap ctid of each record, or NULL (payload = doc id split) */
+    uint32_t n_terms;         /* distinct tokens */
+    const uint8_t *term_key;  /* [n_terms*16] interned keys, strictly ascending (vector.rs:19-35), or NULL when
+                                 callers address terms by dense ordinal (the bm25vector u32-token-id surface) */
+    const uint64_t *post_off; /* [n_terms+1] */
+    const uint32_t *post_doc; /* [P] doc ids, strictly ascending inside a term */
+    const uint32_t *post_tf;  /* [P] term frequencies, != 0 */
+    double k1, b;             /* Bm25IndexOptions (crates/bm25/src/types.rs:18-45): defaults 1.2 / 0.75 */
+} bm25x_corpus;
+
+typedef struct {
+    uint32_t n_docs, n_terms;
+    uint64_t n_postings;
+    uint64_t sum_doc_len;  /* JumpTuple.sum_of_document_lengths (tuples.rs:141-160) */
+    double avgdl, k1, b;
+    uint64_t device_bytes; /* HBM held by the index */
+    uint64_t n_blocks;     /* 128-posting blocks (flush.rs:78-125) */
+    int device;
+} bm25x_index_info;
+
+typedef struct {
+    double kernel_ms;        /* device time of the search kernels, CUDA events on the launch stream */
+    double h2d_ms, d2h_ms;   /* host-API variant only */
+    uint64_t postings;       /* Σ df over live query terms (algorithmic postings touched, exhaustive) */
+    uint64_t bytes_algo;     /* 8 B/posting + 8 B/result slot + 16 B/query term */
+    uint32_t launches;       /* kernels launched */
+    uint32_t queries;        /* live queries (>= 1 known term) */
+} bm25x_search_stats;
+
+/* ---- index lifetime: replaces bm25::build → flush (crates/bm25/src/build.rs:22-71, flush.rs:40-158) for the
+ * read path: lays the postings out in HBM and precomputes per-term s0 and per-fieldnorm s1 (bm25.rs:334-354). */
+int bm25x_index_create(const bm25x_corpus *corpus, int device, bm25x_index **out);
+void bm25x_index_destroy(bm25x_index *idx);
+int bm25x_index_get_info(const bm25x_index *idx, bm25x_index_info *out);
+
+/* address_tokens::read (crates/bm25/src/address_tokens.rs:61-98): key → dense term ordinal,
+ * BM25X_TERM_MISSING when absent (search.rs:60-62 then skips it).  Needs term_key at create time. */
+int bm25x_lookup_terms(const bm25x_index *idx, const uint8_t *keys, uint32_t n, uint32_t *ordinals_out);
+
+/* ---- bm25::search (crates/bm25/src/search.rs:28-282) for a whole batch of queries, called where
+ * DefaultBuilder::build calls it (src/index/bm25/scanners/default.rs:117-129).
+ *   q_off[nq+1], q_terms[]: query i = term ordinals q_terms[q_off[i]..q_off[i+1]) — any order, duplicates and
+ *     BM25X_TERM_MISSING / df==0 terms allowed (they are dropped exactly as search.rs:55-62 drops them).
+ *   k: `limit` (NonZero<usize>, 1..=BM25X_MAX_K).
+ *   allow: optional prefilter bitmap [ceil(n_docs/8)], bit d set ⇒ filter(payload(d)) is true
+ *     (search.rs:230; the per-candidate callback of the reference cannot cross a batch ABI); NULL ⇒ all pass.
+ *   outputs, row i at offset i*k, best first (score desc, then doc id asc — the canonical tie rule):
+ *     out_doc u32, out_score f32 (positive; the SQL binding negates, operators.rs:54),
+ *     out_score64 f64 or NULL (bit-identical to Cache::evaluate summed in ascending term order),
+ *     out_payload u16[3] or NULL, out_n[i] = rows returned (<= k).
+ * Host pointers; the call copies H2D, runs the sm_100a kernels, copies D2H. */
+int bm25x_search_batch(bm25x_index *idx, uint32_t nq, const uint32_t *q_off, const uint32_t *q_terms, uint32_t k,
+                       const uint8_t *allow, uint32_t *out_doc, float *out_score, double *out_score64,
+                       uint16_t *out_payload, uint32_t *out_n, bm25x_search_stats *stats);
+
+/* Split form of the same call, for pipelining and for timing the device part alone:
+ * prepare = canonicalise + upload queries; run = kernels only, everything resident in HBM
+ * (stream = cudaStream_t as void*, NULL = the library's stream; asynchronous unless stats != NULL);
+ * fetch = D2H of the results. */
+int bm25x_batch_prepare(bm25x_index *idx, uint32_t nq, const uint32_t *q_off, const uint32_t *q_terms, uint32_t k,
+                        const uint8_t *allow, bm25x_batch **out);
+int bm25x_batch_run(bm25x_batch *batch, void *stream, bm25x_search_stats *stats);
+int bm25x_batch_fetch(bm25x_batch *batch, uint32_t *out_doc, float *out_score, double *out_score64,
+                      uint16_t *out_payload, uint32_t *out_n);
+void bm25x_batch_destroy(bm25x_batch *batch);
+
+/* ---- bm25::evaluate (crates/bm25/src/evaluate.rs:22-74) behind `<&>` without an index scan
+ * (src/index/operators.rs:22-55): pair p scores document [d_off[p], d_off[p+1]) (sorted distinct term ordinals
+ * with tfs) against query [q_off[p], q_off[p+1]) (sorted distinct ordinals).  out[p] = positive f64 score. */
+int bm25x_evaluate_batch(bm25x_index *idx, uint32_t n_pairs, const uint32_t *d_off, const uint32_t *d_terms,
+                         const uint32_t *d_tfs, const uint32_t *q_off, const uint32_t *q_terms, double *out);
+
+/* ---- synthetic corpus generator (bench/test utility; spec in DESIGN.md, mirrors tests/fuzz:168-205).
+ * Fills a host CSR the caller frees with bm25x_synth_free. zipf_s == 0 ⇒ uniform vocabulary. */
+typedef struct {
+    uint32_t n_docs, n_terms;
+    uint64_t n_postings;
+    uint32_t *doc_len;
+    uint64_t *post_off;
+    uint32_t *post_doc;
+    uint32_t *post_tf;
+} bm25x_synth_corpus;
+int bm25x_synth_generate(uint64_t seed, uint32_t n_docs, uint32_t vocab, uint32_t len_min, uint32_t len_max,
+                         double zipf_s, int nthreads, bm25x_synth_corpus *out);
+void bm25x_synth_free(bm25x_synth_corpus *c);
+/* Queries: n_min..n_max distinct terms with df > 0 drawn from the same distribution. q_off[nq+1], q_terms[nq*n_max]. */
+int bm25x_synth_queries(uint64_t seed, uint32_t nq, uint32_t vocab, uint32_t n_min, uint32_t n_max, double zipf_s,
+                        const uint64_t *post_off, uint32_t *q_off, uint32_t *q_terms);
+
+const char *bm25x_last_error(void);
+int bm25x_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

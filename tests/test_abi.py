@@ -1,0 +1,85 @@
+"""CPU-side checks of the boundary: the C-ABI library loads and exports every symbol include/bm25x.h declares,
+the host logic fails loudly without a GPU (no CPU fallback), and the product's synthetic generator agrees
+bit for bit with the oracle's independent restatement of the same spec."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import _pkg
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def m():
+    mod = _pkg.load()
+    mod.build_library()
+    mod.load_library()
+    return mod
+
+
+def test_exports_every_declared_symbol(m):
+    hdr = open(os.path.join(ROOT, "include", "bm25x.h")).read()
+    names = set(re.findall(r"\b(bm25x_[a-z_0-9]+)\s*\(", hdr))
+    assert len(names) >= 14
+    lib = ctypes.CDLL(os.path.join(ROOT, "vectorchord-bm25_b200", "libbm25x.so"))
+    for n in sorted(names):
+        assert hasattr(lib, n), f"{n} declared in include/bm25x.h but not exported"
+
+
+def test_library_has_only_sm100a_code(m):
+    import subprocess
+    out = subprocess.run(["cuobjdump", "-lelf", os.path.join(ROOT, "vectorchord-bm25_b200", "libbm25x.so")],
+                         capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_no_cpu_fallback(m):
+    if m.device_count() > 0:
+        pytest.skip("GPU present")
+    c = m.synth_corpus(1, 100, 50, 8)
+    with pytest.raises(m.Bm25xError) as e:
+        m.Index.from_corpus(c)
+    assert e.value.code == 2 and "no CPU fallback" in str(e.value)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "vectorchord-bm25_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp", ".h", ".cuh", "Makefile")):
+                assert "oracle" not in open(os.path.join(dp, f)).read().lower().replace(
+                    "the oracle (oracle/bm25_oracle.c) restates the same spec independently; tests compare the two.", ""), f
+
+
+@pytest.mark.parametrize("cfg", [dict(seed=0xB25C0DE1, n=1000, vocab=1000, lmin=32, lmax=32, zipf=0.0),
+                                 dict(seed=5, n=4000, vocab=700, lmin=1, lmax=150, zipf=1.0),
+                                 dict(seed=6, n=2500, vocab=40, lmin=0, lmax=20, zipf=0.7)])
+def test_synth_matches_oracle_generator(m, orc, cfg):
+    a = m.synth_corpus(cfg["seed"], cfg["n"], cfg["vocab"], cfg["lmin"], cfg["lmax"], cfg["zipf"], nthreads=3)
+    b = orc.Corpus.synth(cfg["seed"], cfg["n"], cfg["vocab"], cfg["lmin"], cfg["lmax"], cfg["zipf"])
+    for x in ("doc_len", "post_off", "post_doc", "post_tf"):
+        assert np.array_equal(getattr(a, x), getattr(b, x)), x
+    ix = orc.OracleIndex(b)
+    qa = m.synth_queries(cfg["seed"] + 1000, 64, cfg["vocab"], 1, 8, a.post_off, cfg["zipf"])
+    qb = orc.gen_queries(cfg["seed"] + 1000, 64, cfg["vocab"], 1, 8, ix.df, cfg["zipf"])
+    assert np.array_equal(qa[0], qb[0]) and np.array_equal(qa[1], qb[1])
+    # spec properties: Σ tf = doc length; doc ids ascend inside a term
+    assert int(a.post_tf.astype(np.uint64).sum()) == int(a.doc_len.astype(np.uint64).sum())
+    for t in range(min(cfg["vocab"], 50)):
+        seg = a.post_doc[a.post_off[t]:a.post_off[t + 1]]
+        assert np.all(np.diff(seg.astype(np.int64)) > 0)
+
+
+def test_document_query_types(m):
+    m.Document([1, 5, 9], [1, 2, 3])
+    with pytest.raises(ValueError):
+        m.Document([5, 1], [1, 1])      # not ascending (vector.rs:56-66)
+    with pytest.raises(ValueError):
+        m.Document([1, 2], [1, 0])      # tf == 0
+    with pytest.raises(ValueError):
+        m.Query([3, 3])

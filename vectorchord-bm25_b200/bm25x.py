@@ -1,0 +1,317 @@
+"""ctypes binding of include/bm25x.h (the drop-in C ABI).  No torch types cross this boundary."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libbm25x.so")
+
+MAX_K = 1024
+MAX_QUERY_TERMS = 32
+TERM_MISSING = 0xFFFFFFFF
+
+
+class Bm25xError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"bm25x error {code}: {msg}")
+        self.code = code
+
+
+class _Corpus(C.Structure):
+    _fields_ = [("n_docs", C.c_uint32), ("doc_len", C.POINTER(C.c_uint32)), ("payload", C.POINTER(C.c_uint16)),
+                ("n_terms", C.c_uint32), ("term_key", C.POINTER(C.c_uint8)), ("post_off", C.POINTER(C.c_uint64)),
+                ("post_doc", C.POINTER(C.c_uint32)), ("post_tf", C.POINTER(C.c_uint32)), ("k1", C.c_double),
+                ("b", C.c_double)]
+
+
+class IndexInfo(C.Structure):
+    _fields_ = [("n_docs", C.c_uint32), ("n_terms", C.c_uint32), ("n_postings", C.c_uint64),
+                ("sum_doc_len", C.c_uint64), ("avgdl", C.c_double), ("k1", C.c_double), ("b", C.c_double),
+                ("device_bytes", C.c_uint64), ("n_blocks", C.c_uint64), ("device", C.c_int)]
+
+
+class SearchStats(C.Structure):
+    _fields_ = [("kernel_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double), ("postings", C.c_uint64),
+                ("bytes_algo", C.c_uint64), ("launches", C.c_uint32), ("queries", C.c_uint32)]
+
+
+class _Synth(C.Structure):
+    _fields_ = [("n_docs", C.c_uint32), ("n_terms", C.c_uint32), ("n_postings", C.c_uint64),
+                ("doc_len", C.POINTER(C.c_uint32)), ("post_off", C.POINTER(C.c_uint64)),
+                ("post_doc", C.POINTER(C.c_uint32)), ("post_tf", C.POINTER(C.c_uint32))]
+
+
+def build_library(force: bool = False) -> str:
+    """nvcc -gencode arch=compute_100a,code=sm_100a build of csrc/ → libbm25x.so (in-tree)."""
+    srcdir = os.path.join(_HERE, "csrc")
+    srcs = [os.path.join(srcdir, f) for f in os.listdir(srcdir)] + [os.path.join(_HERE, "..", "include", "bm25x.h")]
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(s) for s in srcs):
+        subprocess.check_call(["make", "-C", srcdir, "-s"], stdout=subprocess.DEVNULL)
+    return _SO
+
+
+_lib = None
+
+
+def load_library():
+    """Loads libbm25x.so; raises (never falls back) when it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_SO):
+        raise Bm25xError(-1, f"{_SO} not built: run `python -c 'import __graft_entry__ as g; g.build()'`")
+    L = C.CDLL(_SO)
+    vp, u8p, u16p, u32p, u64p, f32p, f64p = (C.c_void_p, C.POINTER(C.c_uint8), C.POINTER(C.c_uint16),
+                                             C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_float),
+                                             C.POINTER(C.c_double))
+    L.bm25x_index_create.argtypes = [C.POINTER(_Corpus), C.c_int, C.POINTER(vp)]
+    L.bm25x_index_destroy.argtypes = [vp]
+    L.bm25x_index_destroy.restype = None
+    L.bm25x_index_get_info.argtypes = [vp, C.POINTER(IndexInfo)]
+    L.bm25x_lookup_terms.argtypes = [vp, u8p, C.c_uint32, u32p]
+    L.bm25x_search_batch.argtypes = [vp, C.c_uint32, u32p, u32p, C.c_uint32, u8p, u32p, f32p, f64p, u16p, u32p,
+                                     C.POINTER(SearchStats)]
+    L.bm25x_batch_prepare.argtypes = [vp, C.c_uint32, u32p, u32p, C.c_uint32, u8p, C.POINTER(vp)]
+    L.bm25x_batch_run.argtypes = [vp, vp, C.POINTER(SearchStats)]
+    L.bm25x_batch_fetch.argtypes = [vp, u32p, f32p, f64p, u16p, u32p]
+    L.bm25x_batch_destroy.argtypes = [vp]
+    L.bm25x_batch_destroy.restype = None
+    L.bm25x_evaluate_batch.argtypes = [vp, C.c_uint32, u32p, u32p, u32p, u32p, u32p, f64p]
+    L.bm25x_synth_generate.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_double,
+                                       C.c_int, C.POINTER(_Synth)]
+    L.bm25x_synth_free.argtypes = [C.POINTER(_Synth)]
+    L.bm25x_synth_free.restype = None
+    L.bm25x_synth_queries.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_double, u64p,
+                                      u32p, u32p]
+    L.bm25x_last_error.restype = C.c_char_p
+    L.bm25x_device_count.restype = C.c_int
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise Bm25xError(rc, load_library().bm25x_last_error().decode())
+
+
+def _p(a, ty):
+    return a.ctypes.data_as(C.POINTER(ty)) if a is not None else None
+
+
+def device_count() -> int:
+    return load_library().bm25x_device_count()
+
+
+class Document:
+    """crates/bm25/src/vector.rs:46-98 `Document`: strictly ascending term ordinals with tf != 0."""
+
+    def __init__(self, terms, tfs):
+        self.terms = np.ascontiguousarray(terms, dtype=np.uint32)
+        self.tfs = np.ascontiguousarray(tfs, dtype=np.uint32)
+        if len(self.terms) != len(self.tfs) or np.any(np.diff(self.terms.astype(np.int64)) <= 0) or np.any(self.tfs == 0):
+            raise ValueError("invalid data")  # Document::new → expect("invalid data")
+
+    def length(self) -> int:
+        return int(min(int(self.tfs.astype(np.uint64).sum()), 0xFFFFFFFF))
+
+
+class Query:
+    """crates/bm25/src/vector.rs:100-134 `Query`: strictly ascending term ordinals."""
+
+    def __init__(self, terms):
+        self.terms = np.ascontiguousarray(terms, dtype=np.uint32)
+        if np.any(np.diff(self.terms.astype(np.int64)) <= 0):
+            raise ValueError("invalid data")
+
+
+class SyntheticCorpus:
+    """Host CSR owned by libbm25x (malloc); numpy views without copying (10 GB at the 10M-doc config)."""
+
+    def __init__(self, raw: _Synth):
+        self._raw = raw
+        self.n_docs, self.n_terms, self.n_postings = raw.n_docs, raw.n_terms, raw.n_postings
+        self.doc_len = np.ctypeslib.as_array(raw.doc_len, shape=(raw.n_docs,))
+        self.post_off = np.ctypeslib.as_array(raw.post_off, shape=(raw.n_terms + 1,))
+        n = max(int(raw.n_postings), 1)
+        self.post_doc = np.ctypeslib.as_array(raw.post_doc, shape=(n,))[:raw.n_postings]
+        self.post_tf = np.ctypeslib.as_array(raw.post_tf, shape=(n,))[:raw.n_postings]
+        self.k1, self.b = 1.2, 0.75
+
+    def free(self):
+        if self._raw is not None:
+            self.doc_len = self.post_off = self.post_doc = self.post_tf = None
+            load_library().bm25x_synth_free(C.byref(self._raw))
+            self._raw = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def synth_corpus(seed, n_docs, vocab, len_min, len_max=None, zipf_s=0.0, nthreads=0) -> SyntheticCorpus:
+    raw = _Synth()
+    _check(load_library().bm25x_synth_generate(seed, n_docs, vocab, len_min, len_min if len_max is None else len_max,
+                                               float(zipf_s), nthreads, C.byref(raw)))
+    return SyntheticCorpus(raw)
+
+
+def synth_queries(seed, nq, vocab, n_min, n_max, post_off, zipf_s=0.0):
+    post_off = np.ascontiguousarray(post_off, dtype=np.uint64)
+    q_off = np.zeros(nq + 1, dtype=np.uint32)
+    q_terms = np.zeros(nq * n_max, dtype=np.uint32)
+    _check(load_library().bm25x_synth_queries(seed, nq, vocab, n_min, n_max, float(zipf_s), _p(post_off, C.c_uint64),
+                                              _p(q_off, C.c_uint32), _p(q_terms, C.c_uint32)))
+    return q_off, q_terms[:q_off[-1]].copy()
+
+
+class Index:
+    """Sealed-segment index resident in one GPU's HBM (bm25x_index_*)."""
+
+    def __init__(self, n_docs, doc_len, n_terms, post_off, post_doc, post_tf, k1=1.2, b=0.75, payload=None,
+                 term_keys=None, device=0):
+        L = load_library()
+        self._keep = [np.ascontiguousarray(doc_len, dtype=np.uint32), np.ascontiguousarray(post_off, dtype=np.uint64),
+                      np.ascontiguousarray(post_doc, dtype=np.uint32), np.ascontiguousarray(post_tf, dtype=np.uint32)]
+        c = _Corpus()
+        c.n_docs, c.n_terms, c.k1, c.b = int(n_docs), int(n_terms), float(k1), float(b)
+        c.doc_len = _p(self._keep[0], C.c_uint32)
+        c.post_off = _p(self._keep[1], C.c_uint64)
+        c.post_doc = _p(self._keep[2], C.c_uint32)
+        c.post_tf = _p(self._keep[3], C.c_uint32)
+        if payload is not None:
+            pl = np.ascontiguousarray(payload, dtype=np.uint16)
+            self._keep.append(pl)
+            c.payload = _p(pl, C.c_uint16)
+        if term_keys is not None:
+            tk = np.ascontiguousarray(term_keys, dtype=np.uint8)
+            self._keep.append(tk)
+            c.term_key = _p(tk, C.c_uint8)
+        h = C.c_void_p()
+        _check(L.bm25x_index_create(C.byref(c), device, C.byref(h)))
+        self.h = h
+        self._keep = None  # the library copied everything to the device
+        self.n_docs, self.n_terms = int(n_docs), int(n_terms)
+
+    @staticmethod
+    def from_corpus(c, device=0, **kw):
+        return Index(c.n_docs, c.doc_len, c.n_terms, c.post_off, c.post_doc, c.post_tf, getattr(c, "k1", 1.2),
+                     getattr(c, "b", 0.75), device=device, **kw)
+
+    def close(self):
+        if getattr(self, "h", None):
+            load_library().bm25x_index_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self) -> IndexInfo:
+        out = IndexInfo()
+        _check(load_library().bm25x_index_get_info(self.h, C.byref(out)))
+        return out
+
+    def lookup_terms(self, keys):
+        keys = np.ascontiguousarray(keys, dtype=np.uint8).reshape(-1, 16)
+        out = np.zeros(len(keys), dtype=np.uint32)
+        _check(load_library().bm25x_lookup_terms(self.h, _p(keys, C.c_uint8), len(keys), _p(out, C.c_uint32)))
+        return out
+
+    # ---- bm25::search for a batch (host buffers in, host buffers out) ----
+    def search_batch(self, q_off, q_terms, k, allow=None, want_f64=True, want_payload=False, out=None):
+        q_off = np.ascontiguousarray(q_off, dtype=np.uint32)
+        q_terms = np.ascontiguousarray(q_terms, dtype=np.uint32)
+        nq = len(q_off) - 1
+        kk = max(int(k), 1)
+        if out is None:
+            out = {"doc": np.empty((nq, kk), np.uint32), "score": np.empty((nq, kk), np.float32),
+                   "score64": np.empty((nq, kk), np.float64) if want_f64 else None,
+                   "payload": np.empty((nq, kk, 3), np.uint16) if want_payload else None,
+                   "n": np.empty(nq, np.uint32)}
+        al = np.ascontiguousarray(allow, dtype=np.uint8) if allow is not None else None
+        st = SearchStats()
+        _check(load_library().bm25x_search_batch(self.h, nq, _p(q_off, C.c_uint32), _p(q_terms, C.c_uint32), int(k),
+                                                 _p(al, C.c_uint8), _p(out["doc"], C.c_uint32),
+                                                 _p(out["score"], C.c_float), _p(out["score64"], C.c_double),
+                                                 _p(out["payload"], C.c_uint16), _p(out["n"], C.c_uint32),
+                                                 C.byref(st)))
+        out["stats"] = st
+        return out
+
+    def search(self, query, k, allow=None):
+        """One query, the shape of bm25::search(&index, k, &query, filter): [(score f64, doc id)] best first."""
+        terms = query.terms if isinstance(query, Query) else np.asarray(query, dtype=np.uint32)
+        r = self.search_batch(np.array([0, len(terms)], np.uint32), terms, k, allow=allow)
+        n = int(r["n"][0])
+        return r["doc"][0, :n].copy(), r["score64"][0, :n].copy()
+
+    def prepare(self, q_off, q_terms, k, allow=None) -> "Batch":
+        return Batch(self, q_off, q_terms, k, allow)
+
+    # ---- bm25::evaluate for a batch of (document, query) pairs ----
+    def evaluate_batch(self, docs, queries):
+        d_off = np.zeros(len(docs) + 1, np.uint32)
+        q_off = np.zeros(len(docs) + 1, np.uint32)
+        for i, (d, q) in enumerate(zip(docs, queries)):
+            d_off[i + 1] = d_off[i] + len(d.terms)
+            q_off[i + 1] = q_off[i] + len(q.terms)
+        cat = lambda xs: np.ascontiguousarray(np.concatenate(xs) if xs else np.zeros(0), dtype=np.uint32)
+        d_terms, d_tfs, q_terms = cat([d.terms for d in docs]), cat([d.tfs for d in docs]), cat([q.terms for q in queries])
+        out = np.zeros(len(docs), np.float64)
+        _check(load_library().bm25x_evaluate_batch(self.h, len(docs), _p(d_off, C.c_uint32), _p(d_terms, C.c_uint32),
+                                                   _p(d_tfs, C.c_uint32), _p(q_off, C.c_uint32),
+                                                   _p(q_terms, C.c_uint32), _p(out, C.c_double)))
+        return out
+
+    def evaluate(self, document: Document, query: Query) -> float:
+        return float(self.evaluate_batch([document], [query])[0])
+
+
+class Batch:
+    """Split form: prepare (canonicalise + upload) / run (kernels only, inputs resident in HBM) / fetch (D2H)."""
+
+    def __init__(self, index: Index, q_off, q_terms, k, allow=None):
+        self.index = index
+        q_off = np.ascontiguousarray(q_off, dtype=np.uint32)
+        q_terms = np.ascontiguousarray(q_terms, dtype=np.uint32)
+        self.nq, self.k = len(q_off) - 1, int(k)
+        al = np.ascontiguousarray(allow, dtype=np.uint8) if allow is not None else None
+        h = C.c_void_p()
+        _check(load_library().bm25x_batch_prepare(index.h, self.nq, _p(q_off, C.c_uint32), _p(q_terms, C.c_uint32),
+                                                  self.k, _p(al, C.c_uint8), C.byref(h)))
+        self.h = h
+
+    def run(self, stream=None, timed=True):
+        st = SearchStats()
+        _check(load_library().bm25x_batch_run(self.h, C.c_void_p(stream) if stream else None,
+                                              C.byref(st) if timed else None))
+        return st
+
+    def fetch(self, want_f64=True, want_payload=False):
+        out = {"doc": np.empty((self.nq, self.k), np.uint32), "score": np.empty((self.nq, self.k), np.float32),
+               "score64": np.empty((self.nq, self.k), np.float64) if want_f64 else None,
+               "payload": np.empty((self.nq, self.k, 3), np.uint16) if want_payload else None,
+               "n": np.empty(self.nq, np.uint32)}
+        _check(load_library().bm25x_batch_fetch(self.h, _p(out["doc"], C.c_uint32), _p(out["score"], C.c_float),
+                                                _p(out["score64"], C.c_double), _p(out["payload"], C.c_uint16),
+                                                _p(out["n"], C.c_uint32)))
+        return out
+
+    def close(self):
+        if getattr(self, "h", None):
+            load_library().bm25x_batch_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,65 @@
+// bm25x_common.h — internal types shared by the host library and the sm_100a kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/bm25x.h"
+
+#define BM25X_BLOCK 128u            // postings per block, as the reference (crates/bm25/src/flush.rs:84)
+#define BM25X_DOC_INF 0xFFFFFFFFu   // exhausted-cursor sentinel, as search.rs:484-496
+
+void bm25x_set_error(const char *fmt, ...);
+
+#define BM25X_CUDA_TRY(expr)                                                                   \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            bm25x_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,  \
+                            __LINE__);                                                         \
+            return _e == cudaErrorMemoryAllocation ? BM25X_ERR_OOM : BM25X_ERR_CUDA;           \
+        }                                                                                      \
+    } while (0)
+
+// A posting as it lives in HBM: 8 bytes, the reference's logical Mapping(doc u32, tf u32)
+// (segment.rs:23-25) with the document's fieldnorm byte folded into the low 8 bits of the
+// second word: w = tf << 8 | fieldnorm(doc).  tf < 2^24 is enforced at index build.
+struct Posting {
+    uint32_t doc;
+    uint32_t w;
+};
+
+// Device-resident index (flat arrays; replaces the reference's 8 KiB pages, tapes and address trees).
+struct DeviceIndex {
+    uint32_t n_docs = 0, n_terms = 0;
+    uint64_t n_post = 0;      // real postings
+    uint64_t n_post_pad = 0;  // incl. one pad slot per odd-length term (16-byte TMA granularity)
+    uint64_t n_blocks = 0;
+    Posting *post = nullptr;        // [n_post_pad] term-major, doc-ascending inside a term
+    uint64_t *post_off = nullptr;   // [n_terms+1] padded offsets (even)
+    uint32_t *df = nullptr;         // [n_terms] TokenTuple.number_of_documents
+    uint64_t *blk_off = nullptr;    // [n_terms+1] first block index of each term
+    uint2 *blk = nullptr;           // [n_blocks] (first doc, last doc) — SummaryTuple.{min,max}_document_id
+    float *s0f = nullptr;           // [n_terms] float(s0)
+    double *s0d = nullptr;          // [n_terms] idf*(k1+1), bm25.rs:348
+    double *s1d = nullptr;          // [256] k1*(1-b+b*len(fn)/avgdl), bm25.rs:349-352
+    float *s1f = nullptr;           // [256]
+    uint8_t *fieldnorm = nullptr;   // [n_docs]
+    uint16_t *payload = nullptr;    // [n_docs*3]
+};
+
+struct bm25x_index {
+    int device = 0;
+    int sm_count = 0;
+    DeviceIndex d;
+    double k1 = 1.2, b = 0.75, avgdl = 0;
+    uint64_t sum_len = 0;
+    uint64_t device_bytes = 0;
+    std::vector<uint32_t> h_df;        // host copy for query canonicalisation
+    std::vector<uint8_t> h_keys;       // [n_terms*16] sorted keys (optional)
+    cudaStream_t stream = nullptr;
+    std::vector<void *> allocs;
+};

@@ -1,0 +1,399 @@
+// bm25x_index.cu — index lifetime: host CSR (the reference's sealed Segment) → flat HBM layout.
+//
+// Replaces, for the read path, bm25::build → flush (crates/bm25/src/build.rs:22-71,
+// crates/bm25/src/flush.rs:40-158): same semantics (N, Σlen → avgdl from exact lengths, per-document
+// quantised fieldnorm, 128-posting blocks in (term, doc) order with min/max doc per block, df per
+// token) but none of its page / tape / address-tree machinery.  Layout in DESIGN.md §3.
+#include <math.h>
+#include <omp.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "bm25x_common.h"
+
+static thread_local char g_err[512] = "";
+
+void bm25x_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char *bm25x_last_error(void) { return g_err; }
+
+extern "C" int bm25x_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+// ---- fieldnorm codec (crates/bm25/src/bm25.rs:15-283): 0..=40 step 1, then groups of 8 whose step
+// doubles per group.  Generated, and pinned against the reference's literal table by the tests. ----
+static uint32_t g_fn_len[256];
+static bool g_fn_ready = false;
+static void fn_init() {
+    if (g_fn_ready) return;
+    int n = 0;
+    for (; n <= 40; n++) g_fn_len[n] = (uint32_t)n;
+    uint32_t v = 40, step = 2;
+    while (n < 256) {
+        for (int i = 0; i < 8 && n < 256; i++) {
+            v += step;
+            g_fn_len[n++] = v;
+        }
+        step *= 2;
+    }
+    g_fn_ready = true;
+}
+uint32_t bm25x_fieldnorm_to_length(uint8_t fn) {
+    fn_init();
+    return g_fn_len[fn];
+}
+uint8_t bm25x_length_to_fieldnorm(uint32_t len) {  // bm25.rs:278-283
+    fn_init();
+    int lo = 0, hi = 256;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (g_fn_len[mid] <= len) lo = mid + 1;
+        else hi = mid;
+    }
+    return (uint8_t)(lo - 1);
+}
+
+// ---- device transforms ----
+
+// CSR chunk → AoS postings at their padded positions, with the fieldnorm byte folded in.
+__global__ void k_build_postings(const uint32_t *__restrict__ c_doc, const uint32_t *__restrict__ c_tf,
+                                 uint64_t chunk_base, uint64_t chunk_n, const uint64_t *__restrict__ off,
+                                 const uint64_t *__restrict__ off_pad, uint32_t n_terms,
+                                 const uint8_t *__restrict__ fieldnorm, Posting *__restrict__ post) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= chunk_n) return;
+    uint64_t gi = chunk_base + i;
+    // term = last t with off[t] <= gi
+    uint32_t lo = 0, hi = n_terms;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi + 1) >> 1;
+        if (off[mid] <= gi) lo = mid;
+        else hi = mid - 1;
+    }
+    uint32_t d = c_doc[i];
+    Posting p;
+    p.doc = d;
+    p.w = (c_tf[i] << 8) | fieldnorm[d];
+    post[off_pad[lo] + (gi - off[lo])] = p;
+}
+
+__global__ void k_pad_slots(const uint64_t *__restrict__ off_pad, const uint32_t *__restrict__ df, uint32_t n_terms,
+                            Posting *__restrict__ post) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_terms) return;
+    if (df[t] & 1u) {
+        Posting p;
+        p.doc = BM25X_DOC_INF;
+        p.w = 0;
+        post[off_pad[t] + df[t]] = p;
+    }
+}
+
+__global__ void k_block_desc(const uint64_t *__restrict__ off_pad, const uint32_t *__restrict__ df,
+                             const uint64_t *__restrict__ blk_off, uint32_t n_terms, uint64_t n_blocks,
+                             const Posting *__restrict__ post, uint2 *__restrict__ blk) {
+    uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_blocks) return;
+    uint32_t lo = 0, hi = n_terms;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi + 1) >> 1;
+        if (blk_off[mid] <= g) lo = mid;
+        else hi = mid - 1;
+    }
+    uint64_t b = g - blk_off[lo];
+    uint64_t first = b * BM25X_BLOCK;
+    uint64_t last = first + BM25X_BLOCK;
+    if (last > df[lo]) last = df[lo];
+    blk[g] = make_uint2(post[off_pad[lo] + first].doc, post[off_pad[lo] + last - 1].doc);
+}
+
+template <typename T>
+static int dev_alloc(bm25x_index *ix, T **p, size_t n) {
+    size_t bytes = sizeof(T) * (n ? n : 1);
+    BM25X_CUDA_TRY(cudaMalloc((void **)p, bytes));
+    ix->allocs.push_back((void *)*p);
+    ix->device_bytes += bytes;
+    return BM25X_OK;
+}
+
+#define TRY(x)                      \
+    do {                            \
+        int _rc = (x);              \
+        if (_rc != BM25X_OK) {      \
+            bm25x_index_destroy(ix); \
+            return _rc;             \
+        }                           \
+    } while (0)
+#define CU(x)                                                                                       \
+    do {                                                                                            \
+        cudaError_t _e = (x);                                                                       \
+        if (_e != cudaSuccess) {                                                                    \
+            bm25x_set_error("%s failed: %s (%s:%d)", #x, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            bm25x_index_destroy(ix);                                                                \
+            return _e == cudaErrorMemoryAllocation ? BM25X_ERR_OOM : BM25X_ERR_CUDA;                \
+        }                                                                                           \
+    } while (0)
+
+extern "C" int bm25x_index_create(const bm25x_corpus *c, int device, bm25x_index **out) {
+    if (!c || !out) {
+        bm25x_set_error("bm25x_index_create: null argument");
+        return BM25X_ERR_INVALID;
+    }
+    *out = nullptr;
+    if (c->n_docs == 0 || c->n_docs == BM25X_DOC_INF || !c->doc_len || !c->post_off ||
+        (c->post_off[c->n_terms] && (!c->post_doc || !c->post_tf))) {
+        bm25x_set_error("bm25x_index_create: empty or malformed corpus");
+        return BM25X_ERR_INVALID;
+    }
+    if (!(c->k1 >= 0.0) || !(c->b >= 0.0 && c->b <= 1.0)) {
+        bm25x_set_error("bm25x_index_create: k1/b out of range");
+        return BM25X_ERR_INVALID;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+        cudaGetLastError();
+        bm25x_set_error("bm25x_index_create: CUDA device %d not available (%d devices); there is no CPU fallback",
+                        device, ndev);
+        return BM25X_ERR_CUDA;
+    }
+    fn_init();
+    const uint32_t N = c->n_docs, T = c->n_terms;
+    const uint64_t P = c->post_off[T];
+
+    // ---- host-side validation of the CSR (the reference panics with "data corruption") ----
+    int bad = 0;  // 1 = ordering/ranges, 2 = tf too large
+#pragma omp parallel for schedule(dynamic, 256) reduction(| : bad)
+    for (uint32_t t = 0; t < T; t++) {
+        uint64_t p0 = c->post_off[t], p1 = c->post_off[t + 1];
+        if (p1 < p0 || p1 > P) {
+            bad |= 1;
+            continue;
+        }
+        if (p1 - p0 > N) bad |= 1;
+        uint32_t prev = 0;
+        for (uint64_t p = p0; p < p1; p++) {
+            uint32_t d = c->post_doc[p], f = c->post_tf[p];
+            if (d >= N || f == 0 || (p > p0 && d <= prev)) bad |= 1;
+            if (f >= (1u << 24)) bad |= 2;
+            prev = d;
+        }
+    }
+    if (bad & 1) {
+        bm25x_set_error("bm25x_index_create: corrupt corpus (doc ids must be < n_docs and strictly ascending per term, tf != 0)");
+        return BM25X_ERR_INVALID;
+    }
+    if (bad & 2) {
+        bm25x_set_error("bm25x_index_create: term frequency >= 2^24 is not supported by the packed posting layout");
+        return BM25X_ERR_UNSUPPORTED;
+    }
+    if (c->term_key) {
+        for (uint32_t t = 1; t < T; t++)
+            if (memcmp(c->term_key + (size_t)(t - 1) * 16, c->term_key + (size_t)t * 16, 16) >= 0) {
+                bm25x_set_error("bm25x_index_create: term_key must be strictly ascending");
+                return BM25X_ERR_INVALID;
+            }
+    }
+
+    bm25x_index *ix = new bm25x_index();
+    ix->device = device;
+    ix->k1 = c->k1;
+    ix->b = c->b;
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        bm25x_set_error("bm25x_index_create: device %d is sm_%d%d; this library only carries sm_100a kernels", device,
+                        prop.major, prop.minor);
+        bm25x_index_destroy(ix);
+        return BM25X_ERR_CUDA;
+    }
+    ix->sm_count = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
+
+    // ---- flush.rs:52-66: N, Σlen (exact), per-doc fieldnorm (quantised), avgdl ----
+    std::vector<uint8_t> h_fn(N);
+    uint64_t sum_len = 0;
+#pragma omp parallel for reduction(+ : sum_len)
+    for (uint32_t d = 0; d < N; d++) {
+        sum_len += c->doc_len[d];
+        h_fn[d] = bm25x_length_to_fieldnorm(c->doc_len[d]);
+    }
+    ix->sum_len = sum_len;
+    ix->avgdl = (double)sum_len / (double)N;
+
+    // ---- per-term df, padded offsets, block offsets, s0 (bm25.rs:285-289,348) ----
+    ix->h_df.resize(T);
+    std::vector<uint64_t> h_off_pad(T + 1), h_blk_off(T + 1);
+    std::vector<double> h_s0d(T);
+    std::vector<float> h_s0f(T);
+    uint64_t pp = 0, nb = 0;
+    for (uint32_t t = 0; t < T; t++) {
+        uint64_t n = c->post_off[t + 1] - c->post_off[t];
+        ix->h_df[t] = (uint32_t)n;
+        h_off_pad[t] = pp;
+        h_blk_off[t] = nb;
+        pp += (n + 1) & ~(uint64_t)1;
+        nb += (n + BM25X_BLOCK - 1) / BM25X_BLOCK;
+        double idf = log(((double)N + 1.0) / ((double)n + 0.5));
+        h_s0d[t] = idf * (c->k1 + 1.0);
+        h_s0f[t] = (float)h_s0d[t];
+    }
+    h_off_pad[T] = pp;
+    h_blk_off[T] = nb;
+    // bm25.rs:349-352 — identical for every term: depends only on (k1, b, avgdl)
+    double h_s1d[256];
+    float h_s1f[256];
+    for (int f = 0; f < 256; f++) {
+        double dl = (double)g_fn_len[f];
+        h_s1d[f] = c->k1 * (1.0 - c->b + c->b * dl / ix->avgdl);
+        h_s1f[f] = (float)h_s1d[f];
+    }
+    if (c->term_key) ix->h_keys.assign(c->term_key, c->term_key + (size_t)T * 16);
+
+    DeviceIndex &d = ix->d;
+    d.n_docs = N;
+    d.n_terms = T;
+    d.n_post = P;
+    d.n_post_pad = pp;
+    d.n_blocks = nb;
+    TRY(dev_alloc(ix, &d.post, pp + 2));
+    TRY(dev_alloc(ix, &d.post_off, (size_t)T + 1));
+    TRY(dev_alloc(ix, &d.df, T));
+    TRY(dev_alloc(ix, &d.blk_off, (size_t)T + 1));
+    TRY(dev_alloc(ix, &d.blk, nb));
+    TRY(dev_alloc(ix, &d.s0f, T));
+    TRY(dev_alloc(ix, &d.s0d, T));
+    TRY(dev_alloc(ix, &d.s1d, 256));
+    TRY(dev_alloc(ix, &d.s1f, 256));
+    TRY(dev_alloc(ix, &d.fieldnorm, N));
+    TRY(dev_alloc(ix, &d.payload, (size_t)N * 3));
+    CU(cudaMemcpy(d.post_off, h_off_pad.data(), sizeof(uint64_t) * (T + 1), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d.blk_off, h_blk_off.data(), sizeof(uint64_t) * (T + 1), cudaMemcpyHostToDevice));
+    if (T) {
+        CU(cudaMemcpy(d.df, ix->h_df.data(), sizeof(uint32_t) * T, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(d.s0d, h_s0d.data(), sizeof(double) * T, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(d.s0f, h_s0f.data(), sizeof(float) * T, cudaMemcpyHostToDevice));
+    }
+    CU(cudaMemcpy(d.s1d, h_s1d, sizeof(h_s1d), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d.s1f, h_s1f, sizeof(h_s1f), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d.fieldnorm, h_fn.data(), N, cudaMemcpyHostToDevice));
+    if (c->payload) {
+        CU(cudaMemcpy(d.payload, c->payload, sizeof(uint16_t) * 3 * (size_t)N, cudaMemcpyHostToDevice));
+    } else {
+        std::vector<uint16_t> pl((size_t)N * 3);
+        for (uint32_t i = 0; i < N; i++) {  // synthetic ctid: (block hi, block lo, offset) of a 291-tuple page
+            uint32_t blkno = i / 291;
+            pl[(size_t)i * 3 + 0] = (uint16_t)(blkno >> 16);
+            pl[(size_t)i * 3 + 1] = (uint16_t)(blkno & 0xFFFF);
+            pl[(size_t)i * 3 + 2] = (uint16_t)(i % 291 + 1);
+        }
+        CU(cudaMemcpy(d.payload, pl.data(), sizeof(uint16_t) * pl.size(), cudaMemcpyHostToDevice));
+    }
+
+    // ---- postings: chunked H2D of the CSR columns + device transform to the padded AoS ----
+    {
+        uint64_t *d_off = nullptr;
+        uint32_t *d_cdoc = nullptr, *d_ctf = nullptr;
+        const uint64_t CH = 64ull << 20;  // postings per chunk
+        uint64_t chn = std::min<uint64_t>(CH, P ? P : 1);
+        cudaError_t e1 = cudaMalloc((void **)&d_off, sizeof(uint64_t) * ((size_t)T + 1));
+        cudaError_t e2 = cudaMalloc((void **)&d_cdoc, sizeof(uint32_t) * chn);
+        cudaError_t e3 = cudaMalloc((void **)&d_ctf, sizeof(uint32_t) * chn);
+        cudaError_t e = e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3);
+        if (e == cudaSuccess) e = cudaMemcpy(d_off, c->post_off, sizeof(uint64_t) * ((size_t)T + 1), cudaMemcpyHostToDevice);
+        for (uint64_t base = 0; base < P && e == cudaSuccess; base += CH) {
+            uint64_t n = std::min<uint64_t>(CH, P - base);
+            e = cudaMemcpy(d_cdoc, c->post_doc + base, sizeof(uint32_t) * n, cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) e = cudaMemcpy(d_ctf, c->post_tf + base, sizeof(uint32_t) * n, cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) {
+                k_build_postings<<<(unsigned)((n + 255) / 256), 256>>>(d_cdoc, d_ctf, base, n, d_off, d.post_off, T,
+                                                                       d.fieldnorm, d.post);
+                e = cudaGetLastError();
+            }
+            if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        }
+        if (e == cudaSuccess && T) {
+            k_pad_slots<<<(T + 255) / 256, 256>>>(d.post_off, d.df, T, d.post);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess && nb) {
+            k_block_desc<<<(unsigned)((nb + 255) / 256), 256>>>(d.post_off, d.df, d.blk_off, T, nb, d.post, d.blk);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        cudaFree(d_off);
+        cudaFree(d_cdoc);
+        cudaFree(d_ctf);
+        if (e != cudaSuccess) {
+            bm25x_set_error("bm25x_index_create: posting upload failed: %s", cudaGetErrorString(e));
+            bm25x_index_destroy(ix);
+            return e == cudaErrorMemoryAllocation ? BM25X_ERR_OOM : BM25X_ERR_CUDA;
+        }
+    }
+    *out = ix;
+    return BM25X_OK;
+}
+
+extern "C" void bm25x_index_destroy(bm25x_index *ix) {
+    if (!ix) return;
+    cudaSetDevice(ix->device);
+    for (void *p : ix->allocs) cudaFree(p);
+    if (ix->stream) cudaStreamDestroy(ix->stream);
+    delete ix;
+}
+
+extern "C" int bm25x_index_get_info(const bm25x_index *ix, bm25x_index_info *out) {
+    if (!ix || !out) {
+        bm25x_set_error("bm25x_index_get_info: null argument");
+        return BM25X_ERR_INVALID;
+    }
+    out->n_docs = ix->d.n_docs;
+    out->n_terms = ix->d.n_terms;
+    out->n_postings = ix->d.n_post;
+    out->sum_doc_len = ix->sum_len;
+    out->avgdl = ix->avgdl;
+    out->k1 = ix->k1;
+    out->b = ix->b;
+    out->device_bytes = ix->device_bytes;
+    out->n_blocks = ix->d.n_blocks;
+    out->device = ix->device;
+    return BM25X_OK;
+}
+
+// address_tokens::read (crates/bm25/src/address_tokens.rs:61-98) over the sorted key array.
+extern "C" int bm25x_lookup_terms(const bm25x_index *ix, const uint8_t *keys, uint32_t n, uint32_t *out) {
+    if (!ix || (!keys && n) || (!out && n)) {
+        bm25x_set_error("bm25x_lookup_terms: null argument");
+        return BM25X_ERR_INVALID;
+    }
+    if (ix->h_keys.empty() && ix->d.n_terms) {
+        bm25x_set_error("bm25x_lookup_terms: index was created without term keys");
+        return BM25X_ERR_INVALID;
+    }
+    const uint8_t *base = ix->h_keys.data();
+    for (uint32_t i = 0; i < n; i++) {
+        const uint8_t *key = keys + (size_t)i * 16;
+        uint32_t lo = 0, hi = ix->d.n_terms;
+        while (lo < hi) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (memcmp(base + (size_t)mid * 16, key, 16) < 0) lo = mid + 1;
+            else hi = mid;
+        }
+        out[i] = (lo < ix->d.n_terms && memcmp(base + (size_t)lo * 16, key, 16) == 0) ? lo : BM25X_TERM_MISSING;
+    }
+    return BM25X_OK;
+}
