@@ -1,0 +1,284 @@
+#!/usr/bin/env python
+"""bench.py — BM25 top-k queries/sec on the 10M-doc synthetic corpus (BASELINE.json metric).
+
+One "step" = one pass of the hot path over one batch of synthetic queries.
+  value     : whole-job queries/s with the prepared batch already resident in HBM (kernels only, CUDA events)
+  e2e       : the same through the C-ABI call with HOST buffers (canonicalise + H2D + kernels + D2H) per step
+  roofline  : algorithmic bytes of the search kernel ÷ its device time vs the measured HBM copy peak
+  cpu_baseline / --impl reference : the restated reference algorithm (Block-max WAND, oracle/) on the host cores
+
+Launch: `python bench.py --gpus N --steps K --warmup W` (N>1: under torchrun, one rank per GPU; queries are
+sharded across ranks with the index replicated — weak scaling: every rank runs its own full batch).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs; the metric is quoted on the 10M-doc corpus, top-10
+    "c3": dict(docs=10_000_000, vocab=100_000, doclen=128, queries=100_000, tmin=3, tmax=3, zipf=0.0, k=10,
+               seed=0xB25C0DE0 + 3, desc="C3: 10M docs, vocab 100k uniform, 128 terms/doc, 100k 3-term OR queries"),
+    "c2": dict(docs=1_000_000, vocab=30_000, doclen=64, queries=10_000, tmin=1, tmax=1, zipf=0.0, k=10,
+               seed=0xB25C0DE0 + 2, desc="C2: 1M docs, vocab 30k, 64 terms/doc, 10k 1-term queries"),
+    "c1": dict(docs=1_000, vocab=1_000, doclen=32, queries=100, tmin=3, tmax=3, zipf=0.0, k=10,
+               seed=0xB25C0DE0 + 1, desc="C1: 1k docs, 100 3-term queries"),
+    "c4": dict(docs=10_000_000, vocab=100_000, doclen=128, queries=1_000, tmin=8, tmax=8, zipf=1.0, k=10,
+               seed=0xB25C0DE0 + 4, desc="C4: 10M docs Zipf(1), 8-term queries, exhaustive (1000-query subset)"),
+    "c5": dict(docs=50_000_000, vocab=100_000, doclen=128, queries=100_000, tmin=1, tmax=8, zipf=0.0, k=10,
+               seed=0xB25C0DE0 + 5, desc="C5: 50M docs, mixed 1-8 term queries (per-GPU shard of the 1M batch)"),
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--docs", type=int)
+    ap.add_argument("--queries", type=int)
+    ap.add_argument("--k", type=int)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 8:
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_reference(oracle, oix, q_off, q_terms, k, budget_s, threads):
+    """Times the restated reference algorithm (Block-max WAND, search.rs:28-282) on a bounded sample."""
+    nq = len(q_off) - 1
+    pilot = min(nq, max(threads * 4, 64))
+
+    def run(n):
+        sub_off = (q_off[:n + 1] - q_off[0]).astype(np.uint32)
+        t0 = time.perf_counter()
+        _, _, _, st = oix.search_batch(sub_off, q_terms[q_off[0]:q_off[n]], k, nthreads=threads, wand=True)
+        return time.perf_counter() - t0, st
+
+    dt, _ = run(pilot)
+    n = int(min(nq, max(pilot, pilot * budget_s / max(dt, 1e-6))))
+    dt, st = run(n)
+    return n / dt, n, dt, st
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    wl = dict(WORKLOADS[a.workload])
+    if a.docs:
+        wl["docs"] = a.docs
+    if a.queries:
+        wl["queries"] = a.queries
+    if a.k:
+        wl["k"] = a.k
+    k = wl["k"]
+    cores = os.cpu_count() or 1
+
+    if a.impl == "reference" and rank != 0:
+        return  # the reference arm runs on rank 0 only
+    import _pkg
+    m = _pkg.load()
+    m.load_library()
+    gen_threads = max(1, cores // max(world, 1))
+    t0 = time.time()
+    corpus = m.synth_corpus(wl["seed"], wl["docs"], wl["vocab"], wl["doclen"], wl["doclen"], wl["zipf"], gen_threads)
+    # weak scaling: rank r runs its own batch (different query seed per rank), index replicated
+    q_off, q_terms = m.synth_queries(wl["seed"] + 1000 + 7919 * rank, wl["queries"], wl["vocab"], wl["tmin"],
+                                     wl["tmax"], corpus.post_off, wl["zipf"])
+    t_gen = time.time() - t0
+    nq = wl["queries"]
+    config = {"workload": wl["desc"], "n_docs": wl["docs"], "vocab": wl["vocab"], "doc_len": wl["doclen"],
+              "queries_per_gpu_per_step": nq, "terms_per_query": [wl["tmin"], wl["tmax"]], "k": k,
+              "zipf_s": wl["zipf"], "postings": int(corpus.n_postings), "index_replicated": True,
+              "l2": "index (8 B/posting) is far larger than the 126 MB L2; no flush needed",
+              "gen_s": round(t_gen, 1)}
+
+    if a.impl == "reference":
+        from oracle import oracle
+        oracle.build()
+        oc = oracle.Corpus(corpus.n_docs, corpus.doc_len, corpus.n_terms, corpus.post_off, corpus.post_doc,
+                           corpus.post_tf)
+        oix = oracle.OracleIndex(oc)
+        per_step_budget = min(a.cpu_seconds, 120.0 / max(1, a.steps + a.warmup))
+        qps0, n, dt, _ = cpu_reference(oracle, oix, q_off, q_terms, k, per_step_budget, cores)
+        sub_off = q_off[:n + 1].astype(np.uint32)
+        for _ in range(max(0, a.warmup - 1)):
+            oix.search_batch(sub_off, q_terms[:q_off[n]], k, nthreads=cores, wand=True)
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            oix.search_batch(sub_off, q_terms[:q_off[n]], k, nthreads=cores, wand=True)
+        el = time.perf_counter() - t0
+        qps = n * a.steps / el
+        line = {"impl": "reference", "metric": "queries/sec, 10M-doc synthetic corpus, top-10", "value": qps,
+                "unit": "queries/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": 1e3 * el / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
+                                 "sample": f"{n} of the {nq} queries per step, Block-max WAND restatement "
+                                           f"(oracle/bm25_oracle.c), OpenMP over queries"},
+                "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    t0 = time.time()
+    index = m.Index.from_corpus(corpus, device=local_rank)
+    t_index = time.time() - t0
+    config["index_build_s"] = round(t_index, 1)
+    info = index.info()
+
+    cpu_baseline = None
+    if rank == 0 and a.gpus == 1 and not a.no_cpu_baseline:
+        from oracle import oracle
+        oracle.build()
+        oc = oracle.Corpus(corpus.n_docs, corpus.doc_len, corpus.n_terms, corpus.post_off, corpus.post_doc,
+                           corpus.post_tf)
+        oix = oracle.OracleIndex(oc)
+        qps, n, dt, st = cpu_reference(oracle, oix, q_off, q_terms, k, a.cpu_seconds, cores)
+        qps1, n1, dt1, _ = cpu_reference(oracle, oix, q_off, q_terms, k, a.cpu_seconds / 3, 1)
+        cpu_baseline = {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
+                        "sample": f"first {n} of the {nq} queries ({dt:.1f} s), Block-max WAND restatement of "
+                                  f"crates/bm25/src/search.rs (oracle/bm25_oracle.c), one query per OpenMP thread",
+                        "single_thread_qps": qps1,
+                        "wand_postings_touched_frac": st.postings_touched / max(1, sum(
+                            int(corpus.post_off[t + 1] - corpus.post_off[t]) for t in q_terms[:q_off[n]]))}
+        del oix, oc
+
+    stream = torch.cuda.Stream()  # a real (non-default) stream: the handle is passed through the C ABI
+    torch.cuda.set_stream(stream)
+    batch = index.prepare(q_off, q_terms, k)
+    # ---- value: prepared batch resident in HBM, kernels only ----
+    for _ in range(a.warmup):
+        batch.run(stream=stream.cuda_stream, timed=False)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(a.steps):
+        batch.run(stream=stream.cuda_stream, timed=False)
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    ms_total = ev0.elapsed_time(ev1)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    st = batch.run(stream=stream.cuda_stream, timed=True)  # per-launch kernel time + algorithmic bytes
+    kernel_ms_samples = [batch.run(stream=stream.cuda_stream, timed=True).kernel_ms for _ in range(3)]
+    res_dev = batch.fetch(want_f64=False)
+
+    # ---- e2e: host buffers in, host buffers out, every step ----
+    out = {"doc": np.empty((nq, k), np.uint32), "score": np.empty((nq, k), np.float32), "score64": None,
+           "payload": None, "n": np.empty(nq, np.uint32)}
+    index.search_batch(q_off, q_terms, k, want_f64=False, out=out)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e2e_steps = max(3, min(a.steps, 10))
+    for _ in range(e2e_steps):
+        index.search_batch(q_off, q_terms, k, want_f64=False, out=out)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop()
+    assert np.array_equal(out["doc"], res_dev["doc"]) and np.array_equal(out["n"], res_dev["n"])
+
+    t = torch.tensor([ms_total, 1e3 * e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    ms_step = ms_total / a.steps
+    value = world * nq / (ms_step / 1e3)
+    e2e_value = world * nq * e2e_steps / (e2e_ms / 1e3)
+    peak, peak_src = hbm_peak()
+    kms = statistics.mean(kernel_ms_samples)
+    achieved = st.bytes_algo / (kms / 1e3) / 1e9
+    h2d = 4 * (len(q_off) + len(q_terms) + nq)       # class-grouped ids + offsets + terms
+    d2h = nq * k * 8 + nq * 4
+    line = {"metric": "queries/sec, 10M-doc synthetic corpus, top-10 (+ achieved HBM GB/s in `roofline`)",
+            "value": value, "unit": "queries/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 filter + f64 exact re-score (u32 doc ids)", "data": "synthetic", "config": config,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": f"k_search<M={wl['tmax']}>",
+                         "kernel_ms": kms, "algorithmic_bytes_per_launch": int(st.bytes_algo),
+                         "postings_per_launch": int(st.postings)},
+            "cpu_baseline": cpu_baseline,
+            "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / e2e_steps, "note": "bm25x_search_batch: host q_off/q_terms in, "
+                    "host doc ids + f32 scores + counts out (pageable host buffers)"},
+            "gpu_launches": int(st.launches) * a.steps, "clocks": clocks,
+            "index": {"device_bytes": int(info.device_bytes), "blocks": int(info.n_blocks), "avgdl": info.avgdl}}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

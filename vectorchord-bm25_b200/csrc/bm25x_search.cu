@@ -46,7 +46,13 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t by
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     uint32_t addr = smem_u32(bar);
     uint32_t ok;
+#ifdef BM25X_WATCHDOG
+    uint32_t spins = 0;
+#endif
     do {
+#ifdef BM25X_WATCHDOG
+        if (++spins > (1u << 26)) __trap();  // debug builds: turn a pipeline deadlock into a launch failure
+#endif
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -410,13 +416,13 @@ __device__ void consumer(const SearchParams &p, uint8_t *smem, int tid) {
                             }
                         }
                     }
-                    if (dmin == INF) {
-                        done = true;
-                        break;
-                    }
                     cur = dmin;
                     F = 0.f;
                     cnt = 0;
+                }
+                if (dmin == INF) {  // every sub-run of my bucket is exhausted (also the empty-bucket case)
+                    done = true;
+                    break;
                 }
                 // consume the head posting of run jm: Cache::evaluate (bm25.rs:355-358) in f32
                 {
@@ -766,6 +772,7 @@ extern "C" int bm25x_batch_prepare(bm25x_index *ix, uint32_t nq, const uint32_t 
         cudaMemcpyAsync(b->d_allow, allow, nb, cudaMemcpyHostToDevice, st);
     }
     size_t slots = (size_t)nq * k;
+    if (slots == 0) slots = 1;
     BTRY(batch_alloc(b, &b->d_out_doc, slots));
     BTRY(batch_alloc(b, &b->d_out_score, slots));
     BTRY(batch_alloc(b, &b->d_out_score64, slots));
