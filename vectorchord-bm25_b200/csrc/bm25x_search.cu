@@ -25,552 +25,9 @@
 
 #include "bm25x_common.h"
 
+#include "bm25x_search_kernel.cuh"
+
 namespace {
-
-constexpr uint32_t INF = BM25X_DOC_INF;
-constexpr uint32_t FLAG_FIRST = 1u, FLAG_LAST = 2u;
-
-// ---------------------------------------------------------------------------------------------
-// PTX helpers: mbarrier + 1-D bulk async copy (TMA), as in the Blackwell guide §15.
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    uint32_t addr = smem_u32(bar);
-    uint32_t ok;
-#ifdef BM25X_WATCHDOG
-    uint32_t spins = 0;
-#endif
-    do {
-#ifdef BM25X_WATCHDOG
-        if (++spins > (1u << 26)) __trap();  // debug builds: turn a pipeline deadlock into a launch failure
-#endif
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(addr), "r"(parity)
-            : "memory");
-    } while (!ok);
-}
-__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(smem_dst)),
-                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
-// ---------------------------------------------------------------------------------------------
-struct SearchParams {
-    const Posting *post;
-    const uint64_t *post_off;
-    const uint32_t *df;
-    const uint64_t *blk_off;
-    const uint2 *blk;
-    const float *s0f;
-    const double *s0d;
-    const double *s1d;
-    const float *s1f;
-    const uint16_t *payload;
-    uint32_t n_docs;
-    // one launch = the queries of one term-count class
-    const uint32_t *q_ids;    // original query index
-    const uint32_t *q_off;    // [nq+1]
-    const uint32_t *q_terms;  // canonical: ascending, distinct, df > 0
-    uint32_t nq;
-    uint32_t k;
-    const uint8_t *allow;
-    int *work_counter;
-    uint32_t *out_doc;
-    float *out_score;
-    double *out_score64;
-    uint16_t *out_payload;
-    uint32_t *out_n;
-};
-
-template <int M_>
-struct KCfg {
-    static constexpr int M = M_;                      // max live terms per query in this class
-    static constexpr int T = 256;                     // merge threads (= doc-id buckets per chunk)
-    static constexpr int CB = (M_ <= 8) ? 24 : 32;    // 128-posting blocks per stage (>= M)
-    static constexpr int STAGES = 3;
-    static constexpr int QC = 1024;                   // candidate queue entries per round
-    static constexpr int PC = 2048;                   // pool capacity (>= BM25X_MAX_K + QC)
-    static constexpr int STAGE_POSTINGS = CB * (int)BM25X_BLOCK;
-    static constexpr int THREADS = T + 32;
-    static constexpr int MIN_CTAS = (M_ <= 4) ? 2 : 1;  // register budget: 2 CTAs/SM for the small classes
-};
-
-template <int M>
-struct Hdr {
-    int qid;  // < 0: end of work
-    uint32_t flags, lo, hi, m;
-    uint32_t run_off[M], run_len[M];  // in postings, inside the stage
-    float s0f[M];
-    double s0d[M];
-};
-
-struct Ctrl {
-    int qn, stall, pool_n, thr_valid;
-    float Flo, Fhi;
-    double Sk;
-    uint32_t dk;
-};
-
-template <class C>
-struct Smem {
-    static constexpr size_t stage_bytes = (size_t)C::STAGE_POSTINGS * sizeof(Posting);
-    static constexpr size_t off_stage = 0;
-    static constexpr size_t off_hdr = off_stage + stage_bytes * C::STAGES;
-    static constexpr size_t hdr_bytes = (sizeof(Hdr<C::M>) + 15) & ~(size_t)15;
-    static constexpr size_t off_bar = off_hdr + hdr_bytes * C::STAGES;
-    static constexpr size_t off_bounds = off_bar + 16 * C::STAGES;
-    static constexpr size_t bounds_bytes = (((size_t)C::M * (C::T + 2) * 2) + 15) & ~(size_t)15;
-    static constexpr size_t off_pool_s = off_bounds + bounds_bytes;
-    static constexpr size_t off_pool_d = off_pool_s + (size_t)C::PC * 8;
-    static constexpr size_t off_queue = off_pool_d + (size_t)C::PC * 4;
-    static constexpr size_t off_s1f = off_queue + (size_t)C::QC * 4;
-    static constexpr size_t off_ctrl = off_s1f + 256 * 4;
-    static constexpr size_t total = off_ctrl + ((sizeof(Ctrl) + 15) & ~(size_t)15);
-};
-
-template <int T>
-__device__ __forceinline__ void cbar() {  // barrier over the merge threads only (producer warp excluded)
-    asm volatile("bar.sync 1, %0;" ::"n"(T) : "memory");
-}
-
-__device__ __forceinline__ bool key_before(uint64_t ka, uint32_t da, uint64_t kb, uint32_t db) {
-    return ka > kb || (ka == kb && da < db);  // score desc, doc asc (scores are > 0: raw f64 bits are monotone)
-}
-
-// Bitonic sort of the pool, best first.  n2 = power of two >= n.
-template <int T>
-__device__ void pool_sort(uint64_t *ks, uint32_t *ds, int n, int n2, int tid) {
-    for (int i = n + tid; i < n2; i += T) {
-        ks[i] = 0;
-        ds[i] = INF;
-    }
-    cbar<T>();
-    for (int size = 2; size <= n2; size <<= 1) {
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int i = tid; i < (n2 >> 1); i += T) {
-                int a = 2 * i - (i & (stride - 1));
-                int b = a + stride;
-                uint64_t ka = ks[a], kb = ks[b];
-                uint32_t da = ds[a], db = ds[b];
-                bool desc = (a & size) == 0;
-                bool sw = desc ? key_before(kb, db, ka, da) : key_before(ka, da, kb, db);
-                if (sw) {
-                    ks[a] = kb;
-                    ks[b] = ka;
-                    ds[a] = db;
-                    ds[b] = da;
-                }
-            }
-            cbar<T>();
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-template <class C>
-__device__ void producer(const SearchParams &p, uint8_t *smem, int lane) {
-    constexpr int M = C::M;
-    using S = Smem<C>;
-    uint64_t *full = (uint64_t *)(smem + S::off_bar);
-    uint64_t *empty = full + C::STAGES;
-    int stage = 0;
-    uint32_t phase = 0;
-    for (;;) {
-        int qi = 0;
-        if (lane == 0) qi = atomicAdd(p.work_counter, 1);
-        qi = __shfl_sync(0xFFFFFFFFu, qi, 0);
-        if (qi >= (int)p.nq) break;
-        const uint32_t qid = p.q_ids[qi];
-        const uint32_t t0 = p.q_off[qi];
-        const uint32_t m = p.q_off[qi + 1] - t0;  // 1..M
-        uint32_t dfj = 0, nb = 0;
-        uint64_t pbase = 0, bbase = 0;
-        float s0f = 0.f;
-        double s0d = 0.0;
-        if (lane < (int)m) {
-            uint32_t term = p.q_terms[t0 + lane];
-            dfj = p.df[term];
-            pbase = p.post_off[term];
-            bbase = p.blk_off[term];
-            nb = (dfj + BM25X_BLOCK - 1) / BM25X_BLOCK;
-            s0f = p.s0f[term];
-            s0d = p.s0d[term];
-        }
-        // block quota per term ∝ df: Σ quota <= CB
-        uint64_t sumdf = dfj;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sumdf += __shfl_xor_sync(0xFFFFFFFFu, sumdf, o);
-        const uint32_t quota = lane < (int)m ? 1u + (uint32_t)(((uint64_t)(C::CB - m) * dfj) / sumdf) : 0u;
-        uint32_t ib = 0, lo = 0;
-        bool first = true;
-        for (;;) {
-            // window end: the smallest "first doc of the block just past my quota" over the terms
-            uint32_t prop = INF;
-            if (lane < (int)m && ib + quota < nb) prop = p.blk[bbase + ib + quota].x;
-            const uint32_t hi = __reduce_min_sync(0xFFFFFFFFu, prop);
-            uint32_t eb = ib, lastd = 0;
-            if (lane < (int)m) {
-                uint32_t lim = min(nb, ib + quota);
-                for (uint32_t b = ib; b < lim; ++b) {
-                    uint2 d = p.blk[bbase + b];
-                    if (d.x < hi) {
-                        eb = b + 1;
-                        lastd = d.y;
-                    }
-                }
-            }
-            uint32_t len = 0;
-            if (eb > ib) {
-                uint32_t endp = min(eb * BM25X_BLOCK, dfj);
-                len = (endp - ib * BM25X_BLOCK + 1u) & ~1u;  // whole 16-byte units; the odd tail is a pad slot
-            }
-            uint32_t incl = len;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-                if (lane >= o) incl += v;
-            }
-            const uint32_t off = incl - len;
-            const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-            const bool last = hi == INF;
-
-            mbar_wait(&empty[stage], phase ^ 1u);
-            Hdr<M> *h = (Hdr<M> *)(smem + S::off_hdr + S::hdr_bytes * stage);
-            if (lane < M) {
-                h->run_off[lane] = off;
-                h->run_len[lane] = len;
-                h->s0f[lane] = s0f;
-                h->s0d[lane] = s0d;
-            }
-            if (lane == 0) {
-                h->qid = (int)qid;
-                h->flags = (first ? FLAG_FIRST : 0u) | (last ? FLAG_LAST : 0u);
-                h->lo = lo;
-                h->hi = min(hi, p.n_docs);
-                h->m = m;
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive_expect_tx(&full[stage], total * (uint32_t)sizeof(Posting));
-            __syncwarp();
-            if (len > 0) {
-                tma_load_1d(smem + S::off_stage + S::stage_bytes * stage + (size_t)off * sizeof(Posting),
-                            p.post + pbase + (uint64_t)ib * BM25X_BLOCK, len * (uint32_t)sizeof(Posting), &full[stage]);
-            }
-            if (eb > ib) ib = (lastd >= hi) ? eb - 1 : eb;  // keep a block that straddles the window end
-            lo = hi;
-            first = false;
-            if (++stage == C::STAGES) {
-                stage = 0;
-                phase ^= 1u;
-            }
-            if (last) break;
-        }
-    }
-    mbar_wait(&empty[stage], phase ^ 1u);
-    if (lane == 0) {
-        Hdr<M> *h = (Hdr<M> *)(smem + S::off_hdr + S::hdr_bytes * stage);
-        h->qid = -1;
-        mbar_arrive(&full[stage]);
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-template <class C>
-__device__ void consumer(const SearchParams &p, uint8_t *smem, int tid) {
-    constexpr int M = C::M;
-    constexpr int T = C::T;
-    using S = Smem<C>;
-    const int lane = tid & 31;
-    uint64_t *full = (uint64_t *)(smem + S::off_bar);
-    uint64_t *empty = full + C::STAGES;
-    uint16_t *bounds = (uint16_t *)(smem + S::off_bounds);
-    uint64_t *pool_s = (uint64_t *)(smem + S::off_pool_s);
-    uint32_t *pool_d = (uint32_t *)(smem + S::off_pool_d);
-    uint32_t *q_doc = (uint32_t *)(smem + S::off_queue);
-    const float *s1f = (const float *)(smem + S::off_s1f);
-    volatile Ctrl *ctrl = (volatile Ctrl *)(smem + S::off_ctrl);
-    const uint32_t k = p.k;
-    const double kEps = 1.0 / 262144.0;  // 2^-18 > f32 error bound of the filter score
-
-    int stage = 0;
-    uint32_t phase = 0;
-    for (;;) {
-        mbar_wait(&full[stage], phase);
-        const Hdr<M> *h = (const Hdr<M> *)(smem + S::off_hdr + S::hdr_bytes * stage);
-        const int qid = h->qid;
-        if (qid < 0) break;
-        const uint32_t flags = h->flags;
-        const uint32_t m = h->m;
-        const Posting *st = (const Posting *)(smem + S::off_stage + S::stage_bytes * stage);
-        if (flags & FLAG_FIRST) {
-            if (tid == 0) {
-                ctrl->pool_n = 0;
-                ctrl->thr_valid = 0;
-                ctrl->qn = 0;
-                ctrl->stall = 0;
-            }
-        }
-        // ---- phase 0: bucket boundaries of every run, one pass over the postings ----
-        {
-            const uint32_t lo = h->lo, hi = h->hi;
-            const uint64_t span = (uint64_t)hi - lo;  // >= 1
-            const uint64_t mult = ((uint64_t)T << 32) / span;
-            auto keyb = [&](uint32_t d) -> uint32_t {
-                if (d < lo) return 0u;
-                if (d >= hi) return (uint32_t)T + 1u;
-                return 1u + (uint32_t)(((uint64_t)(d - lo) * mult) >> 32);
-            };
-#pragma unroll 1
-            for (int j = 0; j < M; ++j) {
-                const uint32_t off = h->run_off[j], len = h->run_len[j];
-                uint16_t *B = bounds + j * (T + 2);
-                for (uint32_t i = tid; i <= len; i += T) {
-                    uint32_t kc = i < len ? keyb(st[off + i].doc) : (uint32_t)T + 1u;
-                    uint32_t kp = i == 0 ? 0u : keyb(st[off + i - 1].doc);
-                    for (uint32_t c = kp + 1; c <= kc; ++c) B[c] = (uint16_t)(off + i);
-                }
-            }
-        }
-        cbar<T>();
-        // ---- merge state: heads of my bucket's sub-runs in registers ----
-        uint32_t hd[M], hw[M], pp[M], pe[M];
-        float s0r[M];
-#pragma unroll
-        for (int j = 0; j < M; ++j) {
-            pp[j] = bounds[j * (T + 2) + tid + 1];
-            pe[j] = bounds[j * (T + 2) + tid + 2];
-            s0r[j] = h->s0f[j];
-            hd[j] = INF;
-            hw[j] = 0;
-            if (pp[j] < pe[j]) {
-                Posting v = st[pp[j]];
-                hd[j] = v.doc;
-                hw[j] = v.w;
-            }
-        }
-        uint32_t cur = INF, cnt = 0, lj = 0, lw = 0;
-        float F = 0.f;
-        bool done = false;
-        for (;;) {  // rounds: phase A (merge + filter) → phase B (exact re-score) → pool upkeep
-            const bool tv = ctrl->thr_valid != 0;
-            const float Flo = ctrl->Flo, Fhi = ctrl->Fhi;
-            const double Sk = ctrl->Sk;
-            const uint32_t dk = ctrl->dk;
-            uint32_t cj = INF, cw = 0;  // single-term signature known to score exactly Sk
-            while (!done) {
-                uint32_t dmin = hd[0], wm = hw[0];
-                float s0m = s0r[0];
-                int jm = 0;
-#pragma unroll
-                for (int j = 1; j < M; ++j) {
-                    bool lt = hd[j] < dmin;  // strict: equal docs are consumed in ascending term order
-                    dmin = lt ? hd[j] : dmin;
-                    wm = lt ? hw[j] : wm;
-                    s0m = lt ? s0r[j] : s0m;
-                    jm = lt ? j : jm;
-                }
-                if (dmin != cur) {
-                    if (cur != INF) {  // document `cur` is complete: filter
-                        bool pass = true;
-                        if (tv) {
-                            if (F < Flo) {
-                                pass = false;
-                            } else if (cnt == 1) {
-                                bool tie = lj == cj && lw == cw;
-                                if (!tie && F <= Fhi) {
-                                    double tfd = (double)(lw >> 8);
-                                    double Sx = __ddiv_rn(__dmul_rn(tfd, h->s0d[lj]), __dadd_rn(tfd, p.s1d[lw & 0xFFu]));
-                                    if (Sx == Sk) {
-                                        cj = lj;
-                                        cw = lw;
-                                        tie = true;
-                                    } else if (Sx < Sk) {
-                                        pass = false;
-                                    }
-                                }
-                                if (tie && cur > dk) pass = false;  // equal score, larger doc id: cannot enter
-                            }
-                        }
-                        if (pass) {
-                            int idx = atomicAdd((int *)&ctrl->qn, 1);
-                            if (idx < C::QC) {
-                                q_doc[idx] = cur;
-                            } else {
-                                ctrl->stall = 1;  // queue full: retry this document after the drain
-                                break;
-                            }
-                        }
-                    }
-                    cur = dmin;
-                    F = 0.f;
-                    cnt = 0;
-                }
-                if (dmin == INF) {  // every sub-run of my bucket is exhausted (also the empty-bucket case)
-                    done = true;
-                    break;
-                }
-                // consume the head posting of run jm: Cache::evaluate (bm25.rs:355-358) in f32
-                {
-                    float tff = (float)(wm >> 8);
-                    F += __fdividef(tff * s0m, tff + s1f[wm & 0xFFu]);
-                    cnt++;
-                    lj = (uint32_t)jm;
-                    lw = wm;
-                }
-                uint32_t np = 0, ne = 0;
-#pragma unroll
-                for (int j = 0; j < M; ++j) {
-                    if (j == jm) {
-                        pp[j] += 1;
-                        np = pp[j];
-                        ne = pe[j];
-                    }
-                }
-                uint32_t nd = INF, nw = 0;
-                if (np < ne) {
-                    Posting v = st[np];
-                    nd = v.doc;
-                    nw = v.w;
-                }
-#pragma unroll
-                for (int j = 0; j < M; ++j) {
-                    if (j == jm) {
-                        hd[j] = nd;
-                        hw[j] = nw;
-                    }
-                }
-            }
-            cbar<T>();
-            // ---- phase B: exact f64 score of the survivors, reference operation order ----
-            const int nqueue = min(ctrl->qn, C::QC);
-            const int stalled = ctrl->stall;
-            for (int c = tid; c < nqueue; c += T) {
-                const uint32_t doc = q_doc[c];
-                if (p.allow && !((p.allow[doc >> 3] >> (doc & 7u)) & 1u)) continue;  // filter(payload), search.rs:230
-                double Sx = 0.0;
-                for (uint32_t j = 0; j < m; ++j) {
-                    const uint32_t a = h->run_off[j];
-                    uint32_t l = 0, r = h->run_len[j];
-                    while (l < r) {
-                        uint32_t mid = (l + r) >> 1;
-                        if (st[a + mid].doc < doc) l = mid + 1;
-                        else r = mid;
-                    }
-                    if (l < h->run_len[j]) {
-                        Posting v = st[a + l];
-                        if (v.doc == doc) {
-                            double tfd = (double)(v.w >> 8);
-                            Sx = __dadd_rn(Sx, __ddiv_rn(__dmul_rn(tfd, h->s0d[j]), __dadd_rn(tfd, p.s1d[v.w & 0xFFu])));
-                        }
-                    }
-                }
-                if (!tv || Sx > Sk || (Sx == Sk && doc < dk)) {
-                    int idx = atomicAdd((int *)&ctrl->pool_n, 1);
-                    pool_s[idx] = (uint64_t)__double_as_longlong(Sx);
-                    pool_d[idx] = doc;
-                }
-            }
-            cbar<T>();
-            // ---- pool upkeep ----
-            const int pn = ctrl->pool_n;
-            const bool fin = !stalled && (flags & FLAG_LAST);
-            const int slack = (int)k > 64 ? (int)k : 64;
-            const bool need = pn > 0 && (fin || pn > C::PC - C::QC || pn >= (int)k + slack);
-            if (tid == 0) {
-                ctrl->qn = 0;
-                ctrl->stall = 0;
-            }
-            if (need) {
-                int n2 = 2;
-                while (n2 < pn) n2 <<= 1;
-                pool_sort<T>(pool_s, pool_d, pn, n2, tid);
-                if (tid == 0) {
-                    int nn = pn < (int)k ? pn : (int)k;
-                    ctrl->pool_n = nn;
-                    if (nn == (int)k) {
-                        double sk = __longlong_as_double((long long)pool_s[k - 1]);
-                        ctrl->Sk = sk;
-                        ctrl->dk = pool_d[k - 1];
-                        ctrl->Flo = __double2float_rd(sk * (1.0 - kEps));
-                        ctrl->Fhi = __double2float_ru(sk * (1.0 + kEps));
-                        ctrl->thr_valid = 1;
-                    }
-                }
-            }
-            cbar<T>();
-            if (!stalled) break;
-        }
-        if (flags & FLAG_LAST) {  // Results::into_sorted_vec (search.rs:281): the pool is sorted, best first
-            const int n = ctrl->pool_n;
-            const size_t base = (size_t)qid * k;
-            for (int i = tid; i < (int)k; i += T) {
-                uint32_t d = INF;
-                double sc = 0.0;
-                if (i < n) {
-                    d = pool_d[i];
-                    sc = __longlong_as_double((long long)pool_s[i]);
-                }
-                p.out_doc[base + i] = d;
-                p.out_score[base + i] = (float)sc;
-                if (p.out_score64) p.out_score64[base + i] = sc;
-                if (p.out_payload) {
-                    uint16_t a = 0, b = 0, c = 0;
-                    if (i < n) {
-                        a = p.payload[(size_t)d * 3 + 0];
-                        b = p.payload[(size_t)d * 3 + 1];
-                        c = p.payload[(size_t)d * 3 + 2];
-                    }
-                    p.out_payload[(base + i) * 3 + 0] = a;
-                    p.out_payload[(base + i) * 3 + 1] = b;
-                    p.out_payload[(base + i) * 3 + 2] = c;
-                }
-            }
-            if (tid == 0) p.out_n[qid] = (uint32_t)n;
-            cbar<T>();
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[stage]);
-        if (++stage == C::STAGES) {
-            stage = 0;
-            phase ^= 1u;
-        }
-    }
-}
-
-template <class C>
-__global__ void __launch_bounds__(C::THREADS, C::MIN_CTAS) k_search(const __grid_constant__ SearchParams p) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    using S = Smem<C>;
-    const int tid = threadIdx.x;
-    if (tid == 0) {
-        uint64_t *full = (uint64_t *)(smem + S::off_bar);
-        uint64_t *empty = full + C::STAGES;
-        for (int s = 0; s < C::STAGES; ++s) {
-            mbar_init(&full[s], 1);
-            mbar_init(&empty[s], C::T / 32);
-        }
-        mbar_fence_init();
-    }
-    for (int i = tid; i < 256; i += C::THREADS) ((float *)(smem + S::off_s1f))[i] = p.s1f[i];
-    __syncthreads();
-    if (tid >= C::T) producer<C>(p, smem, tid - C::T);
-    else consumer<C>(p, smem, tid);
-}
 
 // ---------------------------------------------------------------------------------------------
 // bm25::evaluate (crates/bm25/src/evaluate.rs:22-74): one thread per (document, query) pair.
