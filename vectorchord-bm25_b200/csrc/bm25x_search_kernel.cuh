@@ -62,6 +62,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
             : "=r"(ok)
             : "r"(addr), "r"(parity)
             : "memory");
+        if (!ok) __nanosleep(40);  // do not burn issue slots of the merge warps while waiting
     } while (!ok);
 }
 __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
@@ -109,7 +110,7 @@ struct KCfg {
     static constexpr int QC = 512;                      // cold path: candidate queue entries per drain
     static constexpr int PC = 2048;                     // pool capacity (power of two >= BM25X_MAX_K + QC)
     static constexpr int QCW = 32;                      // hot path: per-warp candidate / possible-duplicate lists
-    static constexpr int LOG_SW = 12;                   // per-warp tag map slots = 2^LOG_SW bytes
+    static constexpr int LOG_SW = (M_ <= 8) ? 11 : 12;  // per-warp tag map slots = 2^LOG_SW bytes
     static constexpr int STAGE_POSTINGS = CB * (int)BM25X_BLOCK;
     static constexpr int THREADS = T + 64;              // + producer warp + splitter warp
     static constexpr int MIN_CTAS = (M_ <= 8) ? 2 : 1;
@@ -127,10 +128,17 @@ struct Hdr {
 struct Ctrl {
     int qn, stall, pool_n, thr_valid, ovf, prefer_cold;
     int cnt[3];  // hot path: candidates appended by chunk n are counted in cnt[n % 3]
-    float Flo, Fhi;
+    float Flo;
+    uint32_t dk, tie_sig;
     double Sk;
-    uint32_t dk;
 };
+
+// Signature of a single-term document: (run, tf, fieldnorm).  Two documents with the same signature have bit-identical
+// exact scores, so "same signature as the current k-th entry and a larger doc id" can be rejected without arithmetic.
+constexpr uint32_t SIG_NONE = 0xFFFFFFFFu;
+__device__ __forceinline__ uint32_t make_sig(uint32_t j, uint32_t w) {
+    return (w >> 27) ? SIG_NONE : ((j << 27) | w);  // tf >= 2^19 does not fit beside the 5-bit run index
+}
 
 template <class C>
 struct Smem {
@@ -145,7 +153,8 @@ struct Smem {
     static constexpr size_t wb_bytes = (((size_t)C::M * (C::W + 1) * 2) + 15) & ~(size_t)15;
     static constexpr size_t off_pool_s = off_wb + wb_bytes * C::STAGES;
     static constexpr size_t off_pool_d = off_pool_s + (size_t)C::PC * 8;
-    static constexpr size_t off_queue = off_pool_d + (size_t)C::PC * 4;      // cold: QC entries; hot: W x QCW
+    static constexpr size_t off_pool_g = off_pool_d + (size_t)C::PC * 4;     // tie signatures
+    static constexpr size_t off_queue = off_pool_g + (size_t)C::PC * 4;      // cold: QC entries; hot: W x QCW
     static constexpr size_t queue_bytes = (size_t)(C::QC > C::W * C::QCW ? C::QC : C::W * C::QCW) * 4;
     static constexpr size_t off_dup = off_queue + queue_bytes;               // hot: W x QCW
     static constexpr size_t off_s1f = off_dup + (size_t)C::W * C::QCW * 4;
@@ -174,7 +183,9 @@ __device__ __forceinline__ uint32_t slot_of(uint32_t doc) {
 // Cache::evaluate (bm25.rs:355-358) in f32, for the filter only.
 __device__ __forceinline__ float score_f32(uint32_t w, float s0, const float *s1f) {
     float tff = (float)(w >> 8);
-    return __fdividef(tff * s0, tff + s1f[w & 0xFFu]);
+    float r;  // tf + s1 >= 1: no range guard needed around the approximate reciprocal (1 ulp)
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(tff + s1f[w & 0xFFu]));
+    return tff * s0 * r;
 }
 // Cache::evaluate in f64, bit-exact: (tf * s0) / (tf + s1[fieldnorm]).
 __device__ __forceinline__ double score_f64(uint32_t w, double s0, const double *s1d) {
@@ -184,10 +195,11 @@ __device__ __forceinline__ double score_f64(uint32_t w, double s0, const double 
 
 // Bitonic sort of the pool, best first.  n2 = power of two >= n.  Small pools are sorted by warp 0 alone.
 template <int T>
-__device__ void pool_sort(uint64_t *ks, uint32_t *ds, int n, int n2, int tid) {
+__device__ void pool_sort(uint64_t *ks, uint32_t *ds, uint32_t *gs, int n, int n2, int tid) {
     for (int i = n + tid; i < n2; i += T) {
         ks[i] = 0;
         ds[i] = INF;
+        gs[i] = SIG_NONE;
     }
     cbar<T>();
     const bool solo = n2 <= 64;  // 32 compare-exchanges per stage: one warp, __syncwarp between stages
@@ -206,6 +218,9 @@ __device__ void pool_sort(uint64_t *ks, uint32_t *ds, int n, int n2, int tid) {
                     ks[b] = ka;
                     ds[a] = db;
                     ds[b] = da;
+                    uint32_t ga = gs[a];
+                    gs[a] = gs[b];
+                    gs[b] = ga;
                 }
             }
             if (solo) __syncwarp();
@@ -387,7 +402,7 @@ struct Chunk {
     uint32_t m, lo, span;
     uint8_t *maps;  // W private tag maps (hot) / bucket bounds (cold)
     uint64_t *pool_s;
-    uint32_t *pool_d;
+    uint32_t *pool_d, *pool_g;
     uint32_t *queue;
     const float *s1f;
     volatile Ctrl *ctrl;
@@ -408,47 +423,28 @@ __device__ __forceinline__ uint32_t find_in(const Posting *st, uint32_t a, uint3
     return 0u;
 }
 
-// The threshold filter on the f32 score of a complete document.  `cnt` = postings summed; for single-term
-// documents (lj, lw) identify the posting.  Returns true when the document must be re-scored exactly.
+// The threshold filter on the f32 score F of a complete document: F below Sk·(1-2^-18) cannot reach the top-k
+// (f32 error bound); a single-term document with the signature of the current k-th entry has exactly
+// the k-th score and enters only with a smaller doc id.  Everything else is re-scored exactly.
 struct Filter {
     bool tv;
-    float Flo, Fhi;
+    float Flo;
     double Sk;
-    uint32_t dk;
-    uint32_t cj, cw;  // single-term signature known to score exactly Sk (cache)
+    uint32_t dk, tie_sig, tie_dk;  // tie_dk = INF when there is no usable tie signature
 };
-template <class C>
-__device__ __forceinline__ bool filter_pass(Filter &f, const Chunk<C> &c, const SearchParams &p, float F, uint32_t cnt,
-                                            uint32_t lj, uint32_t lw, uint32_t doc) {
-    if (!f.tv) return true;
-    if (F < f.Flo) return false;
-    if (cnt == 1) {
-        bool tie = lj == f.cj && lw == f.cw;
-        if (!tie && F <= f.Fhi) {
-            double Sx = score_f64(lw, c.h->s0d[lj], p.s1d);
-            if (Sx == f.Sk) {
-                f.cj = lj;
-                f.cw = lw;
-                tie = true;
-            } else if (Sx < f.Sk) {
-                return false;
-            }
-        }
-        if (tie && doc > f.dk) return false;  // equal score, larger doc id: cannot enter the top-k
-    }
-    return true;
+__device__ __forceinline__ bool filter_pass(const Filter &f, float F, uint32_t sig, uint32_t doc) {
+    return F >= f.Flo && !(sig == f.tie_sig && doc > f.tie_dk);
 }
 
 template <class C>
 __device__ __forceinline__ Filter load_filter(const Chunk<C> &c) {
     Filter f;
     f.tv = c.ctrl->thr_valid != 0;
-    f.Flo = c.ctrl->Flo;
-    f.Fhi = c.ctrl->Fhi;
+    f.Flo = f.tv ? c.ctrl->Flo : -1.f;  // scores are > 0: -1 lets everything through
+    f.tie_sig = c.ctrl->tie_sig;
     f.Sk = c.ctrl->Sk;
     f.dk = c.ctrl->dk;
-    f.cj = INF;
-    f.cw = 0;
+    f.tie_dk = (f.tv && f.tie_sig != SIG_NONE) ? f.dk : INF;
     return f;
 }
 
@@ -473,7 +469,7 @@ __device__ int upkeep(const Chunk<C> &c, const SearchParams &p, int pn, bool fin
     if (!need) return pn;
     int n2 = 2;
     while (n2 < pn) n2 <<= 1;
-    pool_sort<T>(c.pool_s, c.pool_d, pn, n2, tid);
+    pool_sort<T>(c.pool_s, c.pool_d, c.pool_g, pn, n2, tid);
     cbar<T>();
     const int nn = pn < (int)k ? pn : (int)k;
     if (tid == 0) {
@@ -481,8 +477,8 @@ __device__ int upkeep(const Chunk<C> &c, const SearchParams &p, int pn, bool fin
             double sk = __longlong_as_double((long long)c.pool_s[k - 1]);
             c.ctrl->Sk = sk;
             c.ctrl->dk = c.pool_d[k - 1];
+            c.ctrl->tie_sig = c.pool_g[k - 1];
             c.ctrl->Flo = __double2float_rd(sk * (1.0 - kEps));
-            c.ctrl->Fhi = __double2float_ru(sk * (1.0 + kEps));
             c.ctrl->thr_valid = 1;
         }
     }
@@ -494,7 +490,7 @@ __device__ int upkeep(const Chunk<C> &c, const SearchParams &p, int pn, bool fin
 // Reference order: Cache::evaluate per term (bm25.rs:355-358), terms ascending.
 template <class C, class RA, class RE>
 __device__ __forceinline__ double exact_score(const Chunk<C> &c, const SearchParams &p, uint32_t doc, RA ra, RE re,
-                                              uint32_t &cnt) {
+                                              uint32_t &cnt, uint32_t &sig) {
     double Sx = 0.0;
     cnt = 0;
     for (uint32_t j = 0; j < c.m; ++j) {
@@ -502,6 +498,7 @@ __device__ __forceinline__ double exact_score(const Chunk<C> &c, const SearchPar
         if (w) {
             Sx = __dadd_rn(Sx, score_f64(w, c.h->s0d[j], p.s1d));
             cnt++;
+            sig = make_sig(j, w);
         }
     }
     return Sx;
@@ -581,7 +578,7 @@ __device__ __noinline__ int cold_chunk(const Chunk<C> &c, const SearchParams &p,
                 jm = lt ? j : jm;
             }
             if (dmin != cur) {
-                if (cur != INF && filter_pass(f, c, p, F, cnt, lj, lw, cur)) {
+                if (cur != INF && filter_pass(f, F, cnt == 1 ? make_sig(lj, lw) : SIG_NONE, cur)) {
                     int idx = atomicAdd((int *)&c.ctrl->qn, 1);
                     if (idx < C::QC) {
                         c.queue[idx] = cur;
@@ -632,14 +629,15 @@ __device__ __noinline__ int cold_chunk(const Chunk<C> &c, const SearchParams &p,
         for (int e = tid; e < nqueue; e += T) {
             const uint32_t doc = c.queue[e];
             if (p.allow && !((p.allow[doc >> 3] >> (doc & 7u)) & 1u)) continue;  // filter(payload), search.rs:230
-            uint32_t n = 0;
+            uint32_t n = 0, sig = SIG_NONE;
             double Sx = exact_score(
                 c, p, doc, [&](uint32_t j) { return h->run_off[j]; },
-                [&](uint32_t j) { return h->run_off[j] + h->run_len[j]; }, n);
+                [&](uint32_t j) { return h->run_off[j] + h->run_len[j]; }, n, sig);
             if (!f.tv || Sx > f.Sk || (Sx == f.Sk && doc < f.dk)) {
                 int idx = atomicAdd((int *)&c.ctrl->pool_n, 1);
                 c.pool_s[idx] = (uint64_t)__double_as_longlong(Sx);
                 c.pool_d[idx] = doc;
+                c.pool_g[idx] = n == 1 ? sig : SIG_NONE;
             }
         }
         cbar<T>();
@@ -693,8 +691,7 @@ __device__ __forceinline__ void hot_warp(const Chunk<C> &c, const SearchParams &
             const bool valid = i < e;
             Posting v = st[valid ? i : a];
             const bool dup = valid && map[slot_of<C::LOG_SW>(v.doc)] != tagv;
-            bool cand = false;
-            if (valid && !dup) cand = filter_pass(f, c, p, score_f32(v.w, s0, c.s1f), 1u, j, v.w, v.doc);
+            const bool cand = valid && !dup && filter_pass(f, score_f32(v.w, s0, c.s1f), make_sig(j, v.w), v.doc);
             const uint32_t md = __ballot_sync(0xFFFFFFFFu, dup);
             if (md) {
                 const uint32_t pos = nd + __popc(md & lt_mask);
@@ -739,7 +736,7 @@ __device__ __forceinline__ void hot_warp(const Chunk<C> &c, const SearchParams &
             F += score_f32(w, h->s0f[jj], c.s1f);
             cnt++;
         }
-        const bool cand = owner && filter_pass(f, c, p, F, cnt, j, v.w, v.doc);
+        const bool cand = owner && filter_pass(f, F, cnt == 1 ? make_sig(j, v.w) : SIG_NONE, v.doc);
         const uint32_t mc = __ballot_sync(0xFFFFFFFFu, cand);
         if (mc) {
             const uint32_t pos = nc + __popc(mc & lt_mask);
@@ -758,7 +755,7 @@ __device__ __forceinline__ void hot_warp(const Chunk<C> &c, const SearchParams &
         const uint32_t ent = has ? wq[lane] : 0u;
         const uint32_t doc = st[ent & 0xFFFFu].doc;
         double Sx = 0.0;
-        uint32_t cnt = 0;
+        uint32_t cnt = 0, sig = SIG_NONE;
         for (uint32_t jj = 0; jj < m; ++jj) {
             const uint32_t a = __shfl_sync(0xFFFFFFFFu, my_a, jj), e = __shfl_sync(0xFFFFFFFFu, my_e, jj);
             if (!has) continue;
@@ -766,6 +763,7 @@ __device__ __forceinline__ void hot_warp(const Chunk<C> &c, const SearchParams &
             if (w) {
                 Sx = __dadd_rn(Sx, score_f64(w, h->s0d[jj], p.s1d));
                 cnt++;
+                sig = make_sig(jj, w);
             }
         }
         bool keep = has;
@@ -783,6 +781,7 @@ __device__ __forceinline__ void hot_warp(const Chunk<C> &c, const SearchParams &
                 if (idx < C::PC) {
                     c.pool_s[idx] = (uint64_t)__double_as_longlong(Sx);
                     c.pool_d[idx] = doc;
+                    c.pool_g[idx] = cnt == 1 ? sig : SIG_NONE;
                 } else {
                     c.ctrl->ovf = 1;
                 }
@@ -803,6 +802,7 @@ __device__ void consumer(const SearchParams &p, uint8_t *smem, int tid) {
     c.maps = smem + S::off_map;
     c.pool_s = (uint64_t *)(smem + S::off_pool_s);
     c.pool_d = (uint32_t *)(smem + S::off_pool_d);
+    c.pool_g = (uint32_t *)(smem + S::off_pool_g);
     c.queue = (uint32_t *)(smem + S::off_queue);
     c.s1f = (const float *)(smem + S::off_s1f);
     c.ctrl = (volatile Ctrl *)(smem + S::off_ctrl);
@@ -911,6 +911,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_CTAS) k_search(const __grid
         ctrl->ovf = 0;
         ctrl->prefer_cold = 0;
         ctrl->cnt[0] = ctrl->cnt[1] = ctrl->cnt[2] = 0;
+        ctrl->tie_sig = SIG_NONE;
     }
     for (int i = tid; i < 256; i += C::THREADS) ((float *)(smem + S::off_s1f))[i] = p.s1f[i];
     for (int i = tid; i < (int)(S::map_bytes / 16); i += C::THREADS) ((uint4 *)(smem + S::off_map))[i] = make_uint4(0, 0, 0, 0);
