@@ -78,6 +78,26 @@ int bm25x_index_create(const bm25x_corpus *corpus, int device, bm25x_index **out
 void bm25x_index_destroy(bm25x_index *idx);
 int bm25x_index_get_info(const bm25x_index *idx, bm25x_index_info *out);
 
+/* ---- replication across the GPUs of one box (queries shard, the index is replicated; NCCL broadcast at load
+ * only).  The library stays NCCL-free: it exposes the device arrays, the caller moves the bytes (bench.py uses
+ * torch.distributed.broadcast over NVLink).  Sender: bm25x_index_get_layout.  Receiver: bm25x_index_alloc_replica
+ * with the sender's layout (scalars only are read), fill the arrays named by its own layout, then
+ * bm25x_index_finalize_replica. */
+#define BM25X_N_ARRAYS 11
+typedef struct {
+    uint32_t n_docs, n_terms;
+    uint64_t n_postings, n_postings_padded, n_blocks, sum_doc_len;
+    double k1, b, avgdl;
+    void *dev_ptr[BM25X_N_ARRAYS];     /* device addresses of the index arrays (valid on `device` only) */
+    uint64_t bytes[BM25X_N_ARRAYS];
+    int device;
+} bm25x_index_layout;
+int bm25x_index_get_layout(const bm25x_index *idx, bm25x_index_layout *out);
+int bm25x_index_alloc_replica(const bm25x_index_layout *like, int device, bm25x_index **out);
+int bm25x_index_finalize_replica(bm25x_index *idx);
+/* df of every term (TokenTuple.number_of_documents), host copy. */
+int bm25x_index_get_df(const bm25x_index *idx, uint32_t *df_out);
+
 /* address_tokens::read (crates/bm25/src/address_tokens.rs:61-98): key → dense term ordinal,
  * BM25X_TERM_MISSING when absent (search.rs:60-62 then skips it).  Needs term_key at create time. */
 int bm25x_lookup_terms(const bm25x_index *idx, const uint8_t *keys, uint32_t n, uint32_t *ordinals_out);

@@ -5,8 +5,8 @@ This package is the thin Python host binding used by tests and bench.py; it mirr
 host-side interface for the path (`bm25::search` / `bm25::evaluate`, Document / Query) and never
 falls back to a CPU implementation: if the library or a B200 is missing, calls raise.
 """
-from .bm25x import (Bm25xError, Index, Batch, SearchStats, synth_corpus, synth_queries, load_library, build_library,
+from .bm25x import (Bm25xError, Index, Batch, SearchStats, IndexLayout, synth_corpus, synth_queries, load_library, build_library,
                     device_count, Document, Query, MAX_K, MAX_QUERY_TERMS, TERM_MISSING)
 
-__all__ = ["Bm25xError", "Index", "Batch", "SearchStats", "synth_corpus", "synth_queries", "load_library",
+__all__ = ["Bm25xError", "Index", "Batch", "SearchStats", "IndexLayout", "synth_corpus", "synth_queries", "load_library",
            "build_library", "device_count", "Document", "Query", "MAX_K", "MAX_QUERY_TERMS", "TERM_MISSING"]

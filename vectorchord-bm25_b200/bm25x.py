@@ -34,6 +34,16 @@ class IndexInfo(C.Structure):
                 ("device_bytes", C.c_uint64), ("n_blocks", C.c_uint64), ("device", C.c_int)]
 
 
+N_ARRAYS = 11
+
+
+class IndexLayout(C.Structure):
+    _fields_ = [("n_docs", C.c_uint32), ("n_terms", C.c_uint32), ("n_postings", C.c_uint64),
+                ("n_postings_padded", C.c_uint64), ("n_blocks", C.c_uint64), ("sum_doc_len", C.c_uint64),
+                ("k1", C.c_double), ("b", C.c_double), ("avgdl", C.c_double), ("dev_ptr", C.c_void_p * N_ARRAYS),
+                ("bytes", C.c_uint64 * N_ARRAYS), ("device", C.c_int)]
+
+
 class SearchStats(C.Structure):
     _fields_ = [("kernel_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double), ("postings", C.c_uint64),
                 ("bytes_algo", C.c_uint64), ("launches", C.c_uint32), ("queries", C.c_uint32)]
@@ -73,6 +83,10 @@ def load_library():
     L.bm25x_index_destroy.restype = None
     L.bm25x_index_get_info.argtypes = [vp, C.POINTER(IndexInfo)]
     L.bm25x_lookup_terms.argtypes = [vp, u8p, C.c_uint32, u32p]
+    L.bm25x_index_get_layout.argtypes = [vp, C.POINTER(IndexLayout)]
+    L.bm25x_index_alloc_replica.argtypes = [C.POINTER(IndexLayout), C.c_int, C.POINTER(vp)]
+    L.bm25x_index_finalize_replica.argtypes = [vp]
+    L.bm25x_index_get_df.argtypes = [vp, u32p]
     L.bm25x_search_batch.argtypes = [vp, C.c_uint32, u32p, u32p, C.c_uint32, u8p, u32p, f32p, f64p, u16p, u32p,
                                      C.POINTER(SearchStats)]
     L.bm25x_batch_prepare.argtypes = [vp, C.c_uint32, u32p, u32p, C.c_uint32, u8p, C.POINTER(vp)]
@@ -197,6 +211,33 @@ class Index:
         self.h = h
         self._keep = None  # the library copied everything to the device
         self.n_docs, self.n_terms = int(n_docs), int(n_terms)
+
+    @classmethod
+    def _adopt(cls, handle, n_docs, n_terms):
+        self = cls.__new__(cls)
+        self.h, self._keep, self.n_docs, self.n_terms = handle, None, int(n_docs), int(n_terms)
+        return self
+
+    def layout(self) -> IndexLayout:
+        out = IndexLayout()
+        _check(load_library().bm25x_index_get_layout(self.h, C.byref(out)))
+        return out
+
+    @classmethod
+    def alloc_replica(cls, like: IndexLayout, device: int) -> "Index":
+        """Empty index of the same shape on `device`; fill the arrays of .layout() (e.g. by NCCL broadcast), then
+        call finalize_replica()."""
+        h = C.c_void_p()
+        _check(load_library().bm25x_index_alloc_replica(C.byref(like), device, C.byref(h)))
+        return cls._adopt(h, like.n_docs, like.n_terms)
+
+    def finalize_replica(self):
+        _check(load_library().bm25x_index_finalize_replica(self.h))
+
+    def df(self):
+        out = np.zeros(self.n_terms, np.uint32)
+        _check(load_library().bm25x_index_get_df(self.h, _p(out, C.c_uint32)))
+        return out
 
     @staticmethod
     def from_corpus(c, device=0, **kw):

@@ -374,6 +374,109 @@ extern "C" int bm25x_index_get_info(const bm25x_index *ix, bm25x_index_info *out
     return BM25X_OK;
 }
 
+// ---- replication: expose / adopt the device arrays (the bytes travel by NCCL in the caller) ----
+static void layout_arrays(const bm25x_index *ix, void **ptr, uint64_t *bytes) {
+    const DeviceIndex &d = ix->d;
+    const uint64_t T = d.n_terms, N = d.n_docs;
+    void *p[BM25X_N_ARRAYS] = {d.post, d.post_off, d.df, d.blk_off, d.blk, d.s0f, d.s0d, d.s1d, d.s1f, d.fieldnorm, d.payload};
+    uint64_t b[BM25X_N_ARRAYS] = {sizeof(Posting) * (d.n_post_pad + 2), 8 * (T + 1), 4 * (T ? T : 1), 8 * (T + 1),
+                                  8 * (d.n_blocks ? d.n_blocks : 1), 4 * (T ? T : 1), 8 * (T ? T : 1), 8 * 256, 4 * 256,
+                                  N, 6 * N};
+    for (int i = 0; i < BM25X_N_ARRAYS; i++) {
+        ptr[i] = p[i];
+        bytes[i] = b[i];
+    }
+}
+
+extern "C" int bm25x_index_get_layout(const bm25x_index *ix, bm25x_index_layout *out) {
+    if (!ix || !out) {
+        bm25x_set_error("bm25x_index_get_layout: null argument");
+        return BM25X_ERR_INVALID;
+    }
+    out->n_docs = ix->d.n_docs;
+    out->n_terms = ix->d.n_terms;
+    out->n_postings = ix->d.n_post;
+    out->n_postings_padded = ix->d.n_post_pad;
+    out->n_blocks = ix->d.n_blocks;
+    out->sum_doc_len = ix->sum_len;
+    out->k1 = ix->k1;
+    out->b = ix->b;
+    out->avgdl = ix->avgdl;
+    out->device = ix->device;
+    layout_arrays(ix, out->dev_ptr, out->bytes);
+    return BM25X_OK;
+}
+
+extern "C" int bm25x_index_alloc_replica(const bm25x_index_layout *like, int device, bm25x_index **out) {
+    if (!like || !out) {
+        bm25x_set_error("bm25x_index_alloc_replica: null argument");
+        return BM25X_ERR_INVALID;
+    }
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+        cudaGetLastError();
+        bm25x_set_error("bm25x_index_alloc_replica: CUDA device %d not available; there is no CPU fallback", device);
+        return BM25X_ERR_CUDA;
+    }
+    bm25x_index *ix = new bm25x_index();
+    ix->device = device;
+    ix->k1 = like->k1;
+    ix->b = like->b;
+    ix->avgdl = like->avgdl;
+    ix->sum_len = like->sum_doc_len;
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    ix->sm_count = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
+    DeviceIndex &d = ix->d;
+    d.n_docs = like->n_docs;
+    d.n_terms = like->n_terms;
+    d.n_post = like->n_postings;
+    d.n_post_pad = like->n_postings_padded;
+    d.n_blocks = like->n_blocks;
+    const size_t T = d.n_terms, N = d.n_docs;
+    TRY(dev_alloc(ix, &d.post, d.n_post_pad + 2));
+    TRY(dev_alloc(ix, &d.post_off, T + 1));
+    TRY(dev_alloc(ix, &d.df, T));
+    TRY(dev_alloc(ix, &d.blk_off, T + 1));
+    TRY(dev_alloc(ix, &d.blk, d.n_blocks));
+    TRY(dev_alloc(ix, &d.s0f, T));
+    TRY(dev_alloc(ix, &d.s0d, T));
+    TRY(dev_alloc(ix, &d.s1d, 256));
+    TRY(dev_alloc(ix, &d.s1f, 256));
+    TRY(dev_alloc(ix, &d.fieldnorm, N));
+    TRY(dev_alloc(ix, &d.payload, N * 3));
+    *out = ix;
+    return BM25X_OK;
+}
+
+extern "C" int bm25x_index_finalize_replica(bm25x_index *ix) {
+    if (!ix) {
+        bm25x_set_error("bm25x_index_finalize_replica: null argument");
+        return BM25X_ERR_INVALID;
+    }
+    BM25X_CUDA_TRY(cudaSetDevice(ix->device));
+    ix->h_df.resize(ix->d.n_terms);
+    if (ix->d.n_terms)
+        BM25X_CUDA_TRY(cudaMemcpy(ix->h_df.data(), ix->d.df, sizeof(uint32_t) * ix->d.n_terms, cudaMemcpyDeviceToHost));
+    return BM25X_OK;
+}
+
+extern "C" int bm25x_index_get_df(const bm25x_index *ix, uint32_t *df_out) {
+    if (!ix || (!df_out && ix->d.n_terms)) {
+        bm25x_set_error("bm25x_index_get_df: null argument");
+        return BM25X_ERR_INVALID;
+    }
+    if (ix->h_df.size() != ix->d.n_terms) {
+        bm25x_set_error("bm25x_index_get_df: replica not finalized");
+        return BM25X_ERR_INVALID;
+    }
+    memcpy(df_out, ix->h_df.data(), sizeof(uint32_t) * ix->d.n_terms);
+    return BM25X_OK;
+}
+
 // address_tokens::read (crates/bm25/src/address_tokens.rs:61-98) over the sorted key array.
 extern "C" int bm25x_lookup_terms(const bm25x_index *ix, const uint8_t *keys, uint32_t n, uint32_t *out) {
     if (!ix || (!keys && n) || (!out && n)) {
