@@ -20,12 +20,16 @@
 // Sk·(1-2^-18) where Sk is the exact f64 k-th best so far; the f32 error bound is < 2^-18
 // relative, so no document of the true top-k is ever rejected; everything that
 // survives is ranked by its exact f64 score.
+#include <stdlib.h>
+#include <string.h>
+
 #include <algorithm>
 #include <vector>
 
 #include "bm25x_common.h"
 
 #include "bm25x_search_kernel.cuh"
+#include "bm25x_search_wq.cuh"
 
 namespace {
 
@@ -120,6 +124,38 @@ static int launch_class(const bm25x_index *ix, SearchParams &sp, cudaStream_t st
     kern<<<grid, C::THREADS, S::total, stream>>>(sp);
     BM25X_CUDA_TRY(cudaGetLastError());
     return BM25X_OK;
+}
+
+// kernel v5 (warp per query): k <= 128 and <= 8 live terms
+template <class C>
+static int launch_wq(const bm25x_index *ix, SearchParams &sp, cudaStream_t stream) {
+    static bool configured[64] = {false};
+    auto kern = k_search_wq<C>;
+    if (!configured[ix->device & 63]) {
+        BM25X_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::total));
+        configured[ix->device & 63] = true;
+    }
+    uint32_t grid = (uint32_t)ix->sm_count;
+    uint32_t need = (sp.nq + C::WARPS - 1) / C::WARPS;
+    if (grid > need) grid = need;
+    kern<<<grid, C::THREADS, C::total, stream>>>(sp);
+    BM25X_CUDA_TRY(cudaGetLastError());
+    return BM25X_OK;
+}
+
+template <int M>
+static int launch_wq_k(const bm25x_index *ix, SearchParams &sp, cudaStream_t stream) {
+    if (sp.k <= 32) return launch_wq<WCfg<M, 128>>(ix, sp, stream);
+    return launch_wq<WCfg<M, 256>>(ix, sp, stream);
+}
+
+static bool use_warp_kernel(uint32_t k, int M) {
+    static int forced = -1;  // BM25X_KERNEL=cta forces the CTA-per-query kernel (v4) everywhere
+    if (forced < 0) {
+        const char *e = getenv("BM25X_KERNEL");
+        forced = (e && strcmp(e, "cta") == 0) ? 1 : 0;
+    }
+    return !forced && k <= 128 && M <= 8;
 }
 
 template <typename T>
@@ -293,6 +329,15 @@ extern "C" int bm25x_batch_run(bm25x_batch *b, void *stream_v, bm25x_search_stat
         sp.out_n = b->d_out_n;
         BM25X_CUDA_TRY(cudaMemsetAsync(g.d_counter, 0, sizeof(int), st));
         int rc = BM25X_OK;
+        if (use_warp_kernel(b->k, g.M)) {
+            switch (g.M) {
+                case 1: rc = launch_wq_k<1>(ix, sp, st); break;
+                case 2: rc = launch_wq_k<2>(ix, sp, st); break;
+                case 3: rc = launch_wq_k<3>(ix, sp, st); break;
+                case 4: rc = launch_wq_k<4>(ix, sp, st); break;
+                default: rc = launch_wq_k<8>(ix, sp, st); break;
+            }
+        } else
         switch (g.M) {
             case 1: rc = launch_class<KCfg<1>>(ix, sp, st); break;
             case 2: rc = launch_class<KCfg<2>>(ix, sp, st); break;

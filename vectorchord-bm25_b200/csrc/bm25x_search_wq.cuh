@@ -1,0 +1,500 @@
+// bm25x_search_wq.cuh — kernel v5: one WARP per query (sm_100a), for k <= 128 and <= 8 live terms.
+//
+// Every warp of the persistent grid is a complete, independent query engine: it fetches a query from the global work
+// counter, plans its own doc-id chunks (lane j = term j, same block-quota rule as the CTA kernel), streams them into
+// its private double-buffered shared-memory stages with TMA bulk copies (cp.async.bulk + mbarrier), unites the
+// chunk's runs with its private tag map (mark / test / resolve — see bm25x_search_kernel.cuh), re-scores the
+// survivors of the f32 filter exactly in f64 and keeps its own candidate pool.  No CTA barrier, no producer or
+// splitter warp, no shared pool: nothing a warp does depends on another warp.
+//
+// Exactness is the same argument as the CTA kernel: the f32 filter rejects only F < Sk·(1-2^-18)
+// and exact-score ties by signature; everything else is ranked by (f64 score desc, doc id asc).
+#pragma once
+
+#include "bm25x_search_kernel.cuh"
+
+namespace {
+
+template <int M_, int KP_>
+struct WCfg {
+    static constexpr int M = M_;                    // max live terms (lanes 0..M-1 own the terms)
+    static constexpr int KP = KP_;                  // pool capacity (power of two >= k + LCAP)
+    static constexpr int CB = (M_ <= 2) ? 4 : ((M_ <= 4) ? 8 : 12);  // 128-posting blocks per stage (>= M)
+    static constexpr int NSTG = 2;
+    static constexpr int LOG_S = 12;                // tag map slots (bytes)
+    static constexpr int LCAP = 64;                 // candidate / possible-duplicate list entries
+    static constexpr int STAGE_POSTINGS = (CB + M_) * (int)BM25X_BLOCK;  // + one partially consumed block per run
+    static constexpr size_t stage_bytes = (size_t)STAGE_POSTINGS * sizeof(Posting);
+    // per-warp shared memory
+    static constexpr size_t off_stage = 0;
+    static constexpr size_t off_map = off_stage + stage_bytes * NSTG;
+    static constexpr size_t off_pool_s = off_map + ((size_t)1 << LOG_S);
+    static constexpr size_t off_pool_d = off_pool_s + (size_t)KP * 8;
+    static constexpr size_t off_pool_g = off_pool_d + (size_t)KP * 4;
+    static constexpr size_t off_cand = off_pool_g + (size_t)KP * 4;
+    static constexpr size_t off_dup = off_cand + (size_t)LCAP * 4;
+    static constexpr size_t off_bar = off_dup + (size_t)LCAP * 4;
+    static constexpr size_t warp_bytes = (off_bar + 8 * NSTG + 127) & ~(size_t)127;
+    static constexpr size_t off_s1f = 0;  // CTA-shared: 1 KiB table first, then the warps
+    static constexpr size_t shared_bytes = 1024;
+    static constexpr int WARPS = (int)((227 * 1024 - shared_bytes) / warp_bytes) > 16 ? 16
+                                 : (int)((227 * 1024 - shared_bytes) / warp_bytes);
+    static constexpr size_t total = shared_bytes + warp_bytes * WARPS;
+    static constexpr int THREADS = WARPS * 32;
+};
+
+// One planned chunk: what every lane needs to issue its TMA copy and to process the chunk afterwards.
+struct ChunkPlan {
+    uint32_t lo, hi;     // doc window (hi already clamped to n_docs)
+    uint32_t off, len;   // my run's placement inside the stage (postings); lanes >= m: len 0
+    uint32_t gsrc;       // posting index (inside my term's list) of stage position `off`
+    bool last;
+};
+
+template <class C>
+struct WarpState {
+    // query terms (lane j < m)
+    uint32_t m, dfj, nb, quota_full;
+    uint64_t pbase, bbase;
+    float s0f;
+    double s0d;
+    // chunk planner: gpos = first posting of my term not yet consumed (exact, found by searching the landed chunk)
+    uint32_t gpos, lo, chunk;
+};
+
+// Plans the next chunk.  Loads start at the exact posting where the previous window ended (rounded down to the
+// 16-byte TMA granule) and end on the block boundary chosen by the quota rule, so nothing is scanned twice.
+template <class C>
+__device__ __forceinline__ ChunkPlan plan_chunk(const SearchParams &p, WarpState<C> &w, int lane) {
+    const bool act = lane < (int)w.m && w.gpos < w.dfj;
+    const uint32_t quota = act ? (w.chunk < 2 ? 1u : w.quota_full) : 0u;
+    const uint32_t ib = w.gpos / BM25X_BLOCK;
+    // window end: the smallest "first doc of the block just past my quota" over the terms (one round trip)
+    uint32_t prop = INF;
+    if (act && ib + quota < w.nb) prop = p.blk[w.bbase + ib + quota].x;
+    uint32_t hi = __reduce_min_sync(0xFFFFFFFFu, prop);
+    if (w.chunk == 0 && hi != INF) hi = w.lo + max(1u, (hi - w.lo) >> 2);
+    ChunkPlan c;
+    c.len = 0;
+    c.gsrc = w.gpos & ~1u;
+    if (act) {
+        uint32_t endp = min((ib + quota) * BM25X_BLOCK, w.dfj);
+        c.len = (endp - c.gsrc + 1u) & ~1u;  // whole 16-byte units; an odd tail is the term's pad slot
+    }
+    uint32_t incl = c.len;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    c.off = incl - c.len;
+    c.lo = w.lo;
+    c.hi = min(hi, p.n_docs);
+    c.last = hi == INF;
+    w.lo = hi;
+    w.chunk++;
+    return c;
+}
+
+template <class C>
+__device__ __forceinline__ void issue_chunk(const SearchParams &p, const WarpState<C> &w, const ChunkPlan &c,
+                                            uint8_t *stage, uint64_t *bar, int lane) {
+    const uint32_t total = __reduce_add_sync(0xFFFFFFFFu, c.len);
+    // the stage was last read through the generic proxy by this warp: order those reads before the async-proxy writes
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) mbar_arrive_expect_tx(bar, total * (uint32_t)sizeof(Posting));
+    __syncwarp();
+    if (c.len > 0)
+        tma_load_1d(stage + (size_t)c.off * sizeof(Posting), p.post + w.pbase + c.gsrc, c.len * (uint32_t)sizeof(Posting),
+                    bar);
+}
+
+// Warp-private pool: (score bits, doc, signature), unsorted until pool_cut.
+template <class C>
+struct WPool {
+    uint64_t *s;
+    uint32_t *d, *g;
+};
+
+// Bitonic sort of the warp's pool (n2 = power of two >= n), best first; then keep the best `k`.
+template <class C>
+__device__ __forceinline__ void wpool_sort(const WPool<C> &pl, int n, int lane) {
+    int n2 = 2;
+    while (n2 < n) n2 <<= 1;
+    for (int i = n + lane; i < n2; i += 32) {
+        pl.s[i] = 0;
+        pl.d[i] = INF;
+        pl.g[i] = SIG_NONE;
+    }
+    __syncwarp();
+    for (int size = 2; size <= n2; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = lane; i < (n2 >> 1); i += 32) {
+                int a = 2 * i - (i & (stride - 1));
+                int b = a + stride;
+                uint64_t ka = pl.s[a], kb = pl.s[b];
+                uint32_t da = pl.d[a], db = pl.d[b];
+                bool desc = (a & size) == 0;
+                bool sw = desc ? key_before(kb, db, ka, da) : key_before(ka, da, kb, db);
+                if (sw) {
+                    pl.s[a] = kb;
+                    pl.s[b] = ka;
+                    pl.d[a] = db;
+                    pl.d[b] = da;
+                    uint32_t ga = pl.g[a];
+                    pl.g[a] = pl.g[b];
+                    pl.g[b] = ga;
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+struct WFilter {
+    bool tv;
+    float Flo;
+    double Sk;
+    uint32_t dk, tie_sig, tie_dk;
+};
+__device__ __forceinline__ bool wfilter_pass(const WFilter &f, float F, uint32_t sig, uint32_t doc) {
+    return F >= f.Flo && !(sig == f.tie_sig && doc > f.tie_dk);
+}
+
+template <class C>
+__global__ void __launch_bounds__(C::THREADS, 1) k_search_wq(const __grid_constant__ SearchParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    constexpr int M = C::M;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    float *s1f = (float *)(smem + C::off_s1f);
+    for (int i = threadIdx.x; i < 256; i += C::THREADS) s1f[i] = p.s1f[i];
+    uint8_t *ws = smem + C::shared_bytes + C::warp_bytes * wid;
+    uint8_t *map = ws + C::off_map;
+    WPool<C> pl;
+    pl.s = (uint64_t *)(ws + C::off_pool_s);
+    pl.d = (uint32_t *)(ws + C::off_pool_d);
+    pl.g = (uint32_t *)(ws + C::off_pool_g);
+    uint32_t *cand = (uint32_t *)(ws + C::off_cand);
+    uint32_t *dupl = (uint32_t *)(ws + C::off_dup);
+    uint64_t *bars = (uint64_t *)(ws + C::off_bar);
+    if (lane == 0) {
+        for (int s = 0; s < C::NSTG; ++s) mbar_init(&bars[s], 1);
+        mbar_fence_init();
+    }
+    for (int i = lane; i < (1 << C::LOG_S) / 16; i += 32) ((uint4 *)map)[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    const uint32_t k = p.k;
+    const double kEps = 1.0 / 262144.0;
+    uint32_t parbits = 0;  // mbarrier phase parity per stage (bit s)
+
+    for (;;) {
+        int qi = 0;
+        if (lane == 0) qi = atomicAdd(p.work_counter, 1);
+        qi = __shfl_sync(0xFFFFFFFFu, qi, 0);
+        if (qi >= (int)p.nq) break;
+        const uint32_t qid = p.q_ids[qi];
+        const uint32_t t0 = p.q_off[qi];
+        WarpState<C> w;
+        w.m = p.q_off[qi + 1] - t0;
+        w.dfj = 0;
+        w.nb = 0;
+        w.pbase = w.bbase = 0;
+        w.s0f = 0.f;
+        w.s0d = 0.0;
+        if (lane < (int)w.m) {
+            uint32_t term = p.q_terms[t0 + lane];
+            w.dfj = p.df[term];
+            w.pbase = p.post_off[term];
+            w.bbase = p.blk_off[term];
+            w.nb = (w.dfj + BM25X_BLOCK - 1) / BM25X_BLOCK;
+            w.s0f = p.s0f[term];
+            w.s0d = p.s0d[term];
+        }
+        {
+            uint64_t sumdf = w.dfj;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sumdf += __shfl_xor_sync(0xFFFFFFFFu, sumdf, o);
+            w.quota_full = lane < (int)w.m ? 1u + (uint32_t)(((uint64_t)(C::CB - w.m) * w.dfj) / sumdf) : 0u;
+        }
+        w.gpos = 0;
+        w.lo = 0;
+        w.chunk = 0;
+        const uint32_t m = w.m;
+        // per-query pool / threshold state (warp-uniform registers)
+        int pn = 0;
+        WFilter f;
+        f.tv = false;
+        f.Flo = -1.f;
+        f.Sk = 0.0;
+        f.dk = INF;
+        f.tie_sig = SIG_NONE;
+        f.tie_dk = INF;
+
+        // cut the pool back to k and refresh the threshold
+        auto pool_cut = [&]() {
+            wpool_sort<C>(pl, pn, lane);
+            // drop duplicates (the dense-overlap pass may emit a document twice: equal (score, doc) are adjacent)
+            {
+                int out = 0;
+                for (int base = 0; base < pn; base += 32) {
+                    const int i = base + lane;
+                    uint64_t sv = 0;
+                    uint32_t dv = INF, gv = SIG_NONE;
+                    bool keep = false;
+                    if (i < pn) {
+                        sv = pl.s[i];
+                        dv = pl.d[i];
+                        gv = pl.g[i];
+                        keep = i == 0 || !(pl.s[i - 1] == sv && pl.d[i - 1] == dv);
+                    }
+                    const uint32_t mk = __ballot_sync(0xFFFFFFFFu, keep);
+                    __syncwarp();
+                    if (keep) {
+                        const int o = out + __popc(mk & lt_mask);
+                        pl.s[o] = sv;
+                        pl.d[o] = dv;
+                        pl.g[o] = gv;
+                    }
+                    out += __popc(mk);
+                    __syncwarp();
+                }
+                pn = out;
+            }
+            if (pn > (int)k) pn = (int)k;
+            if (pn == (int)k) {
+                f.Sk = __longlong_as_double((long long)pl.s[k - 1]);
+                f.dk = pl.d[k - 1];
+                f.tie_sig = pl.g[k - 1];
+                f.tie_dk = f.tie_sig != SIG_NONE ? f.dk : INF;
+                f.Flo = __double2float_rd(f.Sk * (1.0 - kEps));
+                f.tv = true;
+            }
+        };
+
+        int stage = 0;
+        // ---- prime the pipeline: plan + issue chunk 0 ----
+        ChunkPlan cur = plan_chunk<C>(p, w, lane);
+        issue_chunk<C>(p, w, cur, ws + C::off_stage + C::stage_bytes * stage, &bars[stage], lane);
+        for (;;) {
+            // ---- wait for the current chunk ----
+            mbar_wait(&bars[stage], (parbits >> stage) & 1u);
+            parbits ^= 1u << stage;
+            const Posting *st = (const Posting *)(ws + C::off_stage + C::stage_bytes * stage);
+            const uint32_t lo = cur.lo, hi = cur.hi;
+            // exact in-window range of my run (lane < m): [my_a, my_e) — one binary search for the window end; the
+            // load started at most one posting before the window start
+            uint32_t my_a = cur.off, my_e = cur.off;
+            if (cur.len > 0) {
+                if (st[my_a].doc < lo) my_a++;
+                uint32_t l = my_a, r = cur.off + cur.len;
+                while (l < r) {
+                    uint32_t mid = (l + r) >> 1;
+                    if (st[mid].doc < hi) l = mid + 1;
+                    else r = mid;
+                }
+                my_e = l;
+                w.gpos = cur.gsrc + (my_e - cur.off);  // first posting of my term at or past the window end
+            }
+            // ---- prefetch: plan + issue the next chunk into the other stage (overlaps the processing below) ----
+            ChunkPlan nxt;
+            nxt.last = true;
+            nxt.len = nxt.off = 0;
+            nxt.lo = nxt.hi = nxt.gsrc = 0;
+            const bool have_next = !cur.last;
+            if (have_next) {
+                nxt = plan_chunk<C>(p, w, lane);
+                issue_chunk<C>(p, w, nxt, ws + C::off_stage + C::stage_bytes * (stage ^ 1), &bars[stage ^ 1], lane);
+            }
+
+            uint32_t nd = 0, nc = 0;  // list lengths (warp-uniform)
+            // exact re-score of the listed candidates → pool
+            auto flush = [&]() {
+                for (uint32_t base = 0; base < nc; base += 32) {
+                    const bool has = base + lane < nc;
+                    const uint32_t ent = has ? cand[base + lane] : 0u;
+                    const uint32_t doc = st[ent & 0xFFFFu].doc;
+                    double Sx = 0.0;
+                    uint32_t cnt = 0, sig = SIG_NONE;
+                    for (uint32_t jj = 0; jj < m; ++jj) {
+                        const uint32_t a = __shfl_sync(0xFFFFFFFFu, my_a, jj), e = __shfl_sync(0xFFFFFFFFu, my_e, jj);
+                        const double s0d = __shfl_sync(0xFFFFFFFFu, w.s0d, jj);
+                        if (!has) continue;
+                        const uint32_t wv = find_in(st, a, e, doc);
+                        if (wv) {
+                            Sx = __dadd_rn(Sx, score_f64(wv, s0d, p.s1d));
+                            cnt++;
+                            sig = make_sig(jj, wv);
+                        }
+                    }
+                    bool keep = has;
+                    if (keep && p.allow && !((p.allow[doc >> 3] >> (doc & 7u)) & 1u)) keep = false;
+                    // a posting whose tag won its slot although other runs hold the document: its twin carries it
+                    if (keep && cnt > 1 && (ent >> 31) == 0 &&
+                        map[slot_of<C::LOG_S>(doc)] == (uint8_t)(((ent >> 16) & 0x7FFFu) + 1u))
+                        keep = false;
+                    keep = keep && (!f.tv || Sx > f.Sk || (Sx == f.Sk && doc < f.dk));
+                    const uint32_t mk = __ballot_sync(0xFFFFFFFFu, keep);
+                    if (keep) {
+                        const int idx = pn + __popc(mk & lt_mask);
+                        pl.s[idx] = (uint64_t)__double_as_longlong(Sx);
+                        pl.d[idx] = doc;
+                        pl.g[idx] = cnt == 1 ? sig : SIG_NONE;
+                    }
+                    pn += __popc(mk);
+                    __syncwarp();
+                    if (pn > C::KP - 32 || pn >= (int)k + 32) pool_cut();
+                }
+                nc = 0;
+            };
+            auto push_cand = [&](bool c, uint32_t ent) {
+                const uint32_t mc = __ballot_sync(0xFFFFFFFFu, c);
+                if (mc) {
+                    if (c) cand[nc + __popc(mc & lt_mask)] = ent;
+                    nc += __popc(mc);
+                    __syncwarp();
+                    if (nc > (uint32_t)C::LCAP - 32) flush();
+                }
+            };
+
+            // ---- A: mark ----
+            for (uint32_t j = 0; j < m; ++j) {
+                const uint32_t a = __shfl_sync(0xFFFFFFFFu, my_a, j), e = __shfl_sync(0xFFFFFFFFu, my_e, j);
+                const uint8_t tagv = (uint8_t)(j + 1);
+                for (uint32_t i = a + lane; i < e; i += 32) map[slot_of<C::LOG_S>(st[i].doc)] = tagv;
+            }
+            __syncwarp();
+            // ---- B: test; score + filter the singles; list the possible duplicates (2 postings per lane) ----
+            bool dense = false;  // dup list overflowed: resolve every posting by search instead
+            for (uint32_t j = 0; j < m && !dense; ++j) {
+                const uint32_t a = __shfl_sync(0xFFFFFFFFu, my_a, j), e = __shfl_sync(0xFFFFFFFFu, my_e, j);
+                const float s0 = __shfl_sync(0xFFFFFFFFu, w.s0f, j);
+                const uint8_t tagv = (uint8_t)(j + 1);
+                for (uint32_t base = a; base < e; base += 64) {
+                    const uint32_t i0 = base + lane, i1 = i0 + 32;
+                    const bool v0 = i0 < e, v1 = i1 < e;
+                    const Posting p0 = st[v0 ? i0 : a], p1 = st[v1 ? i1 : a];
+                    const uint8_t t0 = map[slot_of<C::LOG_S>(p0.doc)], t1 = map[slot_of<C::LOG_S>(p1.doc)];
+                    const float F0 = score_f32(p0.w, s0, s1f), F1 = score_f32(p1.w, s0, s1f);
+                    const bool d0 = v0 && t0 != tagv, d1 = v1 && t1 != tagv;
+                    const bool c0 = v0 && !d0 && wfilter_pass(f, F0, make_sig(j, p0.w), p0.doc);
+                    const bool c1 = v1 && !d1 && wfilter_pass(f, F1, make_sig(j, p1.w), p1.doc);
+                    const uint32_t md0 = __ballot_sync(0xFFFFFFFFu, d0), md1 = __ballot_sync(0xFFFFFFFFu, d1);
+                    if (md0 | md1) {
+                        const uint32_t q0 = nd + __popc(md0 & lt_mask), q1 = nd + __popc(md0) + __popc(md1 & lt_mask);
+                        if (d0 && q0 < (uint32_t)C::LCAP) dupl[q0] = (j << 16) | i0;
+                        if (d1 && q1 < (uint32_t)C::LCAP) dupl[q1] = (j << 16) | i1;
+                        nd += __popc(md0) + __popc(md1);
+                        if (nd > (uint32_t)C::LCAP) {
+                            dense = true;
+                            break;
+                        }
+                    }
+                    if (__any_sync(0xFFFFFFFFu, c0 | c1)) {
+                        push_cand(c0, (j << 16) | i0);
+                        push_cand(c1, (j << 16) | i1);
+                    }
+                }
+            }
+            __syncwarp();
+            if (!dense) {
+                // ---- C: resolve the possible duplicates; exactly one emitter per document ----
+                for (uint32_t base = 0; base < nd; base += 32) {
+                    const bool has = base + lane < nd;
+                    const uint32_t ent = has ? dupl[base + lane] : 0u;
+                    const uint32_t j = ent >> 16;
+                    const Posting v = st[ent & 0xFFFFu];
+                    const uint32_t winner = (uint32_t)map[slot_of<C::LOG_S>(v.doc)] - 1u;
+                    float F = 0.f;
+                    uint32_t cnt = 0;
+                    bool owner = has;
+                    for (uint32_t jj = 0; jj < m; ++jj) {
+                        const uint32_t a = __shfl_sync(0xFFFFFFFFu, my_a, jj), e = __shfl_sync(0xFFFFFFFFu, my_e, jj);
+                        const float s0 = __shfl_sync(0xFFFFFFFFu, w.s0f, jj);
+                        if (!owner) continue;
+                        const uint32_t wv = jj == j ? v.w : find_in(st, a, e, v.doc);
+                        if (!wv) continue;
+                        if (jj < j && jj != winner) {  // a lower run also detected this document: it emits
+                            owner = false;
+                            continue;
+                        }
+                        F += score_f32(wv, s0, s1f);
+                        cnt++;
+                    }
+                    push_cand(owner && wfilter_pass(f, F, cnt == 1 ? make_sig(j, v.w) : SIG_NONE, v.doc), ent);
+                }
+            } else {
+                // ---- dense overlap: every in-window posting looks its document up in the other runs; the posting of
+                // the lowest run holding the document emits it (entries are flagged: no tag-map twin rule) ----
+                // Candidates listed so far carry tag-map semantics: settle them first.  Documents already emitted by B
+                // for this chunk will be emitted again below; pool_cut() removes the duplicates (same doc ⇒ same exact
+                // score ⇒ adjacent after the sort).
+                flush();
+                for (uint32_t j = 0; j < m; ++j) {
+                    const uint32_t a = __shfl_sync(0xFFFFFFFFu, my_a, j), e = __shfl_sync(0xFFFFFFFFu, my_e, j);
+                    for (uint32_t base = a; base < e; base += 32) {
+                        const uint32_t i = base + lane;
+                        Posting v = st[i < e ? i : a];
+                        const bool valid = i < e;
+                        float F = 0.f;
+                        uint32_t cnt = 0;
+                        bool owner = valid;
+                        for (uint32_t jj = 0; jj < m; ++jj) {
+                            const uint32_t aa = __shfl_sync(0xFFFFFFFFu, my_a, jj), ee = __shfl_sync(0xFFFFFFFFu, my_e, jj);
+                            const float s0 = __shfl_sync(0xFFFFFFFFu, w.s0f, jj);
+                            if (!owner) continue;
+                            const uint32_t wv = jj == j ? v.w : find_in(st, aa, ee, v.doc);
+                            if (!wv) continue;
+                            if (jj < j) {
+                                owner = false;
+                                continue;
+                            }
+                            F += score_f32(wv, s0, s1f);
+                            cnt++;
+                        }
+                        push_cand(owner && wfilter_pass(f, F, cnt == 1 ? make_sig(j, v.w) : SIG_NONE, v.doc),
+                                  0x80000000u | (j << 16) | i);
+                    }
+                }
+            }
+            if (nc) flush();
+            // zero the tag map for the next chunk
+            __syncwarp();
+            for (int i = lane; i < (1 << C::LOG_S) / 16; i += 32) ((uint4 *)map)[i] = make_uint4(0, 0, 0, 0);
+            __syncwarp();
+            if (!have_next) break;
+            cur = nxt;
+            stage ^= 1;
+        }
+        // ---- Results::into_sorted_vec (search.rs:281) ----
+        if (pn > 0) pool_cut();
+        const size_t obase = (size_t)qid * k;
+        for (uint32_t i = lane; i < k; i += 32) {
+            uint32_t d = INF;
+            double sc = 0.0;
+            if ((int)i < pn) {
+                d = pl.d[i];
+                sc = __longlong_as_double((long long)pl.s[i]);
+            }
+            p.out_doc[obase + i] = d;
+            p.out_score[obase + i] = (float)sc;
+            if (p.out_score64) p.out_score64[obase + i] = sc;
+            if (p.out_payload) {
+                uint16_t a = 0, b = 0, cc = 0;
+                if ((int)i < pn) {
+                    a = p.payload[(size_t)d * 3 + 0];
+                    b = p.payload[(size_t)d * 3 + 1];
+                    cc = p.payload[(size_t)d * 3 + 2];
+                }
+                p.out_payload[(obase + i) * 3 + 0] = a;
+                p.out_payload[(obase + i) * 3 + 1] = b;
+                p.out_payload[(obase + i) * 3 + 2] = cc;
+            }
+        }
+        if (lane == 0) p.out_n[qid] = (uint32_t)pn;
+        __syncwarp();
+    }
+}
+
+}  // namespace
