@@ -223,6 +223,13 @@ extern "C" int bm25x_index_create(const bm25x_corpus *c, int device, bm25x_index
     }
     ix->sm_count = prop.multiProcessorCount;
     CU(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
+    {   // keep freed batch buffers cached in the default pool (bm25x_batch_* allocate stream-ordered)
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t thr = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+    }
 
     // ---- flush.rs:52-66: N, Σlen (exact), per-doc fieldnorm (quantised), avgdl ----
     std::vector<uint8_t> h_fn(N);
@@ -430,6 +437,13 @@ extern "C" int bm25x_index_alloc_replica(const bm25x_index_layout *like, int dev
     CU(cudaGetDeviceProperties(&prop, device));
     ix->sm_count = prop.multiProcessorCount;
     CU(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
+    {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t thr = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+    }
     DeviceIndex &d = ix->d;
     d.n_docs = like->n_docs;
     d.n_terms = like->n_terms;

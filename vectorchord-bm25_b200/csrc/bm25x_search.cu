@@ -160,7 +160,8 @@ static bool use_warp_kernel(uint32_t k, int M) {
 
 template <typename T>
 static int batch_alloc(bm25x_batch *b, T **p, size_t n) {
-    BM25X_CUDA_TRY(cudaMalloc((void **)p, sizeof(T) * (n ? n : 1)));
+    // stream-ordered allocation from the device's (cached) default pool: no cudaMalloc/cudaFree cost per call
+    BM25X_CUDA_TRY(cudaMallocAsync((void **)p, sizeof(T) * (n ? n : 1), b->ix->stream));
     b->allocs.push_back((void *)*p);
     return BM25X_OK;
 }
@@ -168,7 +169,8 @@ static int batch_alloc(bm25x_batch *b, T **p, size_t n) {
 extern "C" void bm25x_batch_destroy(bm25x_batch *b) {
     if (!b) return;
     cudaSetDevice(b->ix->device);
-    for (void *p : b->allocs) cudaFree(p);
+    if (b->last_stream && b->last_stream != (void *)b->ix->stream) cudaStreamSynchronize((cudaStream_t)b->last_stream);
+    for (void *p : b->allocs) cudaFreeAsync(p, b->ix->stream);
     if (b->ev0) cudaEventDestroy(b->ev0);
     if (b->ev1) cudaEventDestroy(b->ev1);
     delete b;

@@ -154,7 +154,8 @@ __device__ __forceinline__ void wpool_sort(const WPool<C> &pl, int n, int lane) 
 
 struct WFilter {
     bool tv;
-    float Flo;
+    float Flo;   // f32 scores below this cannot reach the top-k
+    float ctf;   // lane j: single-term postings of run j pass iff tf >= ctf * s1[fn]   (the same test, solved for tf)
     double Sk;
     uint32_t dk, tie_sig, tie_dk;
 };
@@ -231,6 +232,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_wq(const __grid_consta
         f.dk = INF;
         f.tie_sig = SIG_NONE;
         f.tie_dk = INF;
+        f.ctf = 0.f;  // no threshold yet: everything passes
 
         // cut the pool back to k and refresh the threshold
         auto pool_cut = [&]() {
@@ -268,7 +270,12 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_wq(const __grid_consta
                 f.dk = pl.d[k - 1];
                 f.tie_sig = pl.g[k - 1];
                 f.tie_dk = f.tie_sig != SIG_NONE ? f.dk : INF;
-                f.Flo = __double2float_rd(f.Sk * (1.0 - kEps));
+                const double flo = f.Sk * (1.0 - kEps);
+                f.Flo = __double2float_rd(flo);
+                // F = s0·tf/(tf+s1) >= flo  ⇔  tf >= flo/(s0-flo)·s1  (s0 > flo), never when s0 <= flo.  Solved in f64
+                // from the exact s0 (no cancellation trouble), shrunk by 2^-20 to stay conservative in f32.
+                f.ctf = __int_as_float(0x7f800000);  // +inf
+                if (lane < (int)m && w.s0d > flo) f.ctf = __double2float_rd(flo / (w.s0d - flo) * (1.0 - 1.0 / 1048576.0));
                 f.tv = true;
             }
         };
@@ -369,17 +376,19 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_wq(const __grid_consta
             bool dense = false;  // dup list overflowed: resolve every posting by search instead
             for (uint32_t j = 0; j < m && !dense; ++j) {
                 const uint32_t a = __shfl_sync(0xFFFFFFFFu, my_a, j), e = __shfl_sync(0xFFFFFFFFu, my_e, j);
-                const float s0 = __shfl_sync(0xFFFFFFFFu, w.s0f, j);
+                const float ctf = __shfl_sync(0xFFFFFFFFu, f.ctf, j);
                 const uint8_t tagv = (uint8_t)(j + 1);
                 for (uint32_t base = a; base < e; base += 64) {
                     const uint32_t i0 = base + lane, i1 = i0 + 32;
                     const bool v0 = i0 < e, v1 = i1 < e;
                     const Posting p0 = st[v0 ? i0 : a], p1 = st[v1 ? i1 : a];
                     const uint8_t t0 = map[slot_of<C::LOG_S>(p0.doc)], t1 = map[slot_of<C::LOG_S>(p1.doc)];
-                    const float F0 = score_f32(p0.w, s0, s1f), F1 = score_f32(p1.w, s0, s1f);
                     const bool d0 = v0 && t0 != tagv, d1 = v1 && t1 != tagv;
-                    const bool c0 = v0 && !d0 && wfilter_pass(f, F0, make_sig(j, p0.w), p0.doc);
-                    const bool c1 = v1 && !d1 && wfilter_pass(f, F1, make_sig(j, p1.w), p1.doc);
+                    // threshold test in the tf domain (no division); signature tie rule as in wfilter_pass
+                    const bool g0 = (float)(p0.w >> 8) >= ctf * s1f[p0.w & 0xFFu];
+                    const bool g1 = (float)(p1.w >> 8) >= ctf * s1f[p1.w & 0xFFu];
+                    const bool c0 = v0 && !d0 && g0 && !(make_sig(j, p0.w) == f.tie_sig && p0.doc > f.tie_dk);
+                    const bool c1 = v1 && !d1 && g1 && !(make_sig(j, p1.w) == f.tie_sig && p1.doc > f.tie_dk);
                     const uint32_t md0 = __ballot_sync(0xFFFFFFFFu, d0), md1 = __ballot_sync(0xFFFFFFFFu, d1);
                     if (md0 | md1) {
                         const uint32_t q0 = nd + __popc(md0 & lt_mask), q1 = nd + __popc(md0) + __popc(md1 & lt_mask);
@@ -400,6 +409,41 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_wq(const __grid_consta
             __syncwarp();
             if (!dense) {
                 // ---- C: resolve the possible duplicates; exactly one emitter per document ----
+                if (nd <= 32) {
+                    // Every run that holds the document but did not win its slot is in the list, so the list itself
+                    // tells which listed postings belong together (MATCH.ANY); only the slot's winner run — whose
+                    // posting, if it is the same document, stayed silent — has to be searched.
+                    const bool has = lane < (int)nd;
+                    const uint32_t ent = has ? dupl[lane] : 0u;
+                    const uint32_t j = ent >> 16;
+                    const Posting v = st[ent & 0xFFFFu];
+                    const unsigned long long key = has ? (unsigned long long)v.doc : ((1ull << 32) | (unsigned)lane);
+                    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);
+                    const uint32_t winner = has ? (uint32_t)map[slot_of<C::LOG_S>(v.doc)] - 1u : 0u;
+                    const float Fm = score_f32(v.w, __shfl_sync(0xFFFFFFFFu, w.s0f, j & 31u), s1f);
+                    float F = 0.f;
+                    uint32_t cnt = 0, rem = peers;
+                    while (__any_sync(0xFFFFFFFFu, rem != 0u)) {  // entries are listed in ascending run order
+                        const int src = rem ? __ffs(rem) - 1 : lane;
+                        const float val = __shfl_sync(0xFFFFFFFFu, Fm, src);
+                        if (rem) {
+                            F += val;
+                            cnt++;
+                            rem &= rem - 1u;
+                        }
+                    }
+                    const bool owner = has && lane == __ffs(peers) - 1;
+                    const uint32_t wa = __shfl_sync(0xFFFFFFFFu, my_a, winner & 31u), we = __shfl_sync(0xFFFFFFFFu, my_e, winner & 31u);
+                    const float ws0 = __shfl_sync(0xFFFFFFFFu, w.s0f, winner & 31u);
+                    if (owner) {
+                        const uint32_t wv = find_in(st, wa, we, v.doc);
+                        if (wv) {
+                            F += score_f32(wv, ws0, s1f);
+                            cnt++;
+                        }
+                    }
+                    push_cand(owner && wfilter_pass(f, F, cnt == 1 ? make_sig(j, v.w) : SIG_NONE, v.doc), ent);
+                } else
                 for (uint32_t base = 0; base < nd; base += 32) {
                     const bool has = base + lane < nd;
                     const uint32_t ent = has ? dupl[base + lane] : 0u;
