@@ -19,8 +19,9 @@ template <int M_, int KP_>
 struct WCfg {
     static constexpr int M = M_;                    // max live terms (lanes 0..M-1 own the terms)
     static constexpr int KP = KP_;                  // pool capacity (power of two >= k + LCAP)
-    static constexpr int CB = (M_ <= 2) ? 4 : ((M_ <= 4) ? 8 : 12);  // 128-posting blocks per stage (>= M)
-    static constexpr int NSTG = 2;
+    // block budget per chunk: quota_j = 1 + floor((CB-m)·df_j/Σdf) → two 128-posting blocks per term for m = M <= 4
+    static constexpr int CB = M_ == 1 ? 2 : (M_ == 2 ? 5 : (M_ == 3 ? 8 : (M_ == 4 ? 11 : 8)));
+    static constexpr int NSTG = 1;                  // stages per warp: 1 = rely on the other warps to hide the load latency
     static constexpr int LOG_S = 12;                // tag map slots (bytes)
     static constexpr int LCAP = 64;                 // candidate / possible-duplicate list entries
     static constexpr int STAGE_POSTINGS = (CB + M_) * (int)BM25X_BLOCK;  // + one partially consumed block per run
@@ -310,7 +311,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_wq(const __grid_consta
             nxt.len = nxt.off = 0;
             nxt.lo = nxt.hi = nxt.gsrc = 0;
             const bool have_next = !cur.last;
-            if (have_next) {
+            if (C::NSTG == 2 && have_next) {
                 nxt = plan_chunk<C>(p, w, lane);
                 issue_chunk<C>(p, w, nxt, ws + C::off_stage + C::stage_bytes * (stage ^ 1), &bars[stage ^ 1], lane);
             }
@@ -508,8 +509,13 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_wq(const __grid_consta
             for (int i = lane; i < (1 << C::LOG_S) / 16; i += 32) ((uint4 *)map)[i] = make_uint4(0, 0, 0, 0);
             __syncwarp();
             if (!have_next) break;
+            if (C::NSTG == 1) {  // single-buffered: the stage is free again only now
+                nxt = plan_chunk<C>(p, w, lane);
+                issue_chunk<C>(p, w, nxt, ws + C::off_stage + C::stage_bytes * stage, &bars[stage], lane);
+            } else {
+                stage ^= 1;
+            }
             cur = nxt;
-            stage ^= 1;
         }
         // ---- Results::into_sorted_vec (search.rs:281) ----
         if (pn > 0) pool_cut();
