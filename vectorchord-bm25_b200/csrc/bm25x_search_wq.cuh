@@ -19,8 +19,8 @@ template <int M_, int KP_>
 struct WCfg {
     static constexpr int M = M_;                    // max live terms (lanes 0..M-1 own the terms)
     static constexpr int KP = KP_;                  // pool capacity (power of two >= k + LCAP)
-    // block budget per chunk: quota_j = 1 + floor((CB-m)·df_j/Σdf) → two 128-posting blocks per term for m = M <= 4
-    static constexpr int CB = M_ == 1 ? 2 : (M_ == 2 ? 5 : (M_ == 3 ? 8 : (M_ == 4 ? 11 : 8)));
+    // block budget per chunk (Σ quota = CB exactly): two 128-posting blocks per term for m = M <= 4
+    static constexpr int CB = M_ <= 4 ? 2 * M_ : M_;
     static constexpr int NSTG = 1;                  // stages per warp: 1 = rely on the other warps to hide the load latency
     static constexpr int LOG_S = 12;                // tag map slots (bytes)
     static constexpr int LCAP = 64;                 // candidate / possible-duplicate list entries
@@ -65,14 +65,24 @@ struct WarpState {
 
 // Plans the next chunk.  Loads start at the exact posting where the previous window ended (rounded down to the
 // 16-byte TMA granule) and end on the block boundary chosen by the quota rule, so nothing is scanned twice.
+// First half of the planner: issue the one global load the plan needs (first doc of the block just past my quota).
+// Called as soon as gpos is known, so that the round trip hides behind the processing of the current chunk.
 template <class C>
-__device__ __forceinline__ ChunkPlan plan_chunk(const SearchParams &p, WarpState<C> &w, int lane) {
+__device__ __forceinline__ uint32_t plan_prefetch(const SearchParams &p, const WarpState<C> &w, int lane) {
     const bool act = lane < (int)w.m && w.gpos < w.dfj;
     const uint32_t quota = act ? (w.chunk < 2 ? 1u : w.quota_full) : 0u;
     const uint32_t ib = w.gpos / BM25X_BLOCK;
-    // window end: the smallest "first doc of the block just past my quota" over the terms (one round trip)
     uint32_t prop = INF;
-    if (act && ib + quota < w.nb) prop = p.blk[w.bbase + ib + quota].x;
+    if (act && ib + quota < w.nb) prop = __ldg(&p.blk[w.bbase + ib + quota].x);
+    return prop;
+}
+
+template <class C>
+__device__ __forceinline__ ChunkPlan plan_chunk(const SearchParams &p, WarpState<C> &w, int lane, uint32_t prop) {
+    const bool act = lane < (int)w.m && w.gpos < w.dfj;
+    const uint32_t quota = act ? (w.chunk < 2 ? 1u : w.quota_full) : 0u;
+    const uint32_t ib = w.gpos / BM25X_BLOCK;
+    // window end: the smallest "first doc of the block just past my quota" over the terms
     uint32_t hi = __reduce_min_sync(0xFFFFFFFFu, prop);
     if (w.chunk == 0 && hi != INF) hi = w.lo + max(1u, (hi - w.lo) >> 2);
     ChunkPlan c;
@@ -218,7 +228,11 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_wq(const __grid_consta
             uint64_t sumdf = w.dfj;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) sumdf += __shfl_xor_sync(0xFFFFFFFFu, sumdf, o);
-            w.quota_full = lane < (int)w.m ? 1u + (uint32_t)(((uint64_t)(C::CB - w.m) * w.dfj) / sumdf) : 0u;
+            // one block each, the rest of the budget ∝ df, the rounding leftover to the first terms
+            const uint32_t extra = (uint32_t)C::CB - w.m;
+            const uint32_t share = lane < (int)w.m ? (uint32_t)(((uint64_t)extra * w.dfj) / sumdf) : 0u;
+            const uint32_t left = extra - __reduce_add_sync(0xFFFFFFFFu, share);
+            w.quota_full = lane < (int)w.m ? 1u + share + (lane < (int)left ? 1u : 0u) : 0u;
         }
         w.gpos = 0;
         w.lo = 0;
@@ -283,7 +297,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_wq(const __grid_consta
 
         int stage = 0;
         // ---- prime the pipeline: plan + issue chunk 0 ----
-        ChunkPlan cur = plan_chunk<C>(p, w, lane);
+        ChunkPlan cur = plan_chunk<C>(p, w, lane, plan_prefetch<C>(p, w, lane));
         issue_chunk<C>(p, w, cur, ws + C::off_stage + C::stage_bytes * stage, &bars[stage], lane);
         for (;;) {
             // ---- wait for the current chunk ----
@@ -311,8 +325,10 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_wq(const __grid_consta
             nxt.len = nxt.off = 0;
             nxt.lo = nxt.hi = nxt.gsrc = 0;
             const bool have_next = !cur.last;
+            uint32_t prop_next = INF;
+            if (have_next) prop_next = plan_prefetch<C>(p, w, lane);  // consumed after the processing below (NSTG == 1)
             if (C::NSTG == 2 && have_next) {
-                nxt = plan_chunk<C>(p, w, lane);
+                nxt = plan_chunk<C>(p, w, lane, prop_next);
                 issue_chunk<C>(p, w, nxt, ws + C::off_stage + C::stage_bytes * (stage ^ 1), &bars[stage ^ 1], lane);
             }
 
@@ -510,7 +526,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_wq(const __grid_consta
             __syncwarp();
             if (!have_next) break;
             if (C::NSTG == 1) {  // single-buffered: the stage is free again only now
-                nxt = plan_chunk<C>(p, w, lane);
+                nxt = plan_chunk<C>(p, w, lane, prop_next);
                 issue_chunk<C>(p, w, nxt, ws + C::off_stage + C::stage_bytes * stage, &bars[stage], lane);
             } else {
                 stage ^= 1;
