@@ -248,6 +248,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_wq(const __grid_consta
         f.tie_sig = SIG_NONE;
         f.tie_dk = INF;
         f.ctf = 0.f;  // no threshold yet: everything passes
+        bool dense_query = false;  // sticky: a chunk of this query needed the dense-overlap path
 
         // cut the pool back to k and refresh the threshold
         auto pool_cut = [&]() {
@@ -338,7 +339,9 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_wq(const __grid_consta
                 for (uint32_t base = 0; base < nc; base += 32) {
                     const bool has = base + lane < nc;
                     const uint32_t ent = has ? cand[base + lane] : 0u;
-                    const uint32_t doc = st[ent & 0xFFFFu].doc;
+                    // entry flavours: (run << 16 | stage position) from the tag-map phases; bit 31 set: no twin rule;
+                    // bits 31+30 set: document given as offset from the window start (dense accumulator path)
+                    const uint32_t doc = (ent >> 30) == 3u ? lo + (ent & 0x3FFFFFFFu) : st[ent & 0xFFFFu].doc;
                     double Sx = 0.0;
                     uint32_t cnt = 0, sig = SIG_NONE;
                     for (uint32_t jj = 0; jj < m; ++jj) {
@@ -382,15 +385,21 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_wq(const __grid_consta
                 }
             };
 
+            // Dense-overlap chunks (head terms: most documents hold several query terms) have a narrow doc window:
+            // when it fits, scores are summed in a dense f32 accumulator indexed by doc - lo (in the tag-map memory).
+            constexpr uint32_t ACC_DOCS = (1u << C::LOG_S) / 4u;
+            const bool can_acc = hi - lo <= ACC_DOCS;
+            bool dense = dense_query && can_acc;  // the previous chunk was dense: skip the tag-map phases right away
             // ---- A: mark ----
-            for (uint32_t j = 0; j < m; ++j) {
-                const uint32_t a = __shfl_sync(0xFFFFFFFFu, my_a, j), e = __shfl_sync(0xFFFFFFFFu, my_e, j);
-                const uint8_t tagv = (uint8_t)(j + 1);
-                for (uint32_t i = a + lane; i < e; i += 32) map[slot_of<C::LOG_S>(st[i].doc)] = tagv;
+            if (!dense) {
+                for (uint32_t j = 0; j < m; ++j) {
+                    const uint32_t a = __shfl_sync(0xFFFFFFFFu, my_a, j), e = __shfl_sync(0xFFFFFFFFu, my_e, j);
+                    const uint8_t tagv = (uint8_t)(j + 1);
+                    for (uint32_t i = a + lane; i < e; i += 32) map[slot_of<C::LOG_S>(st[i].doc)] = tagv;
+                }
+                __syncwarp();
             }
-            __syncwarp();
             // ---- B: test; score + filter the singles; list the possible duplicates (2 postings per lane) ----
-            bool dense = false;  // dup list overflowed: resolve every posting by search instead
             for (uint32_t j = 0; j < m && !dense; ++j) {
                 const uint32_t a = __shfl_sync(0xFFFFFFFFu, my_a, j), e = __shfl_sync(0xFFFFFFFFu, my_e, j);
                 const float ctf = __shfl_sync(0xFFFFFFFFu, f.ctf, j);
@@ -485,12 +494,34 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_wq(const __grid_consta
                     }
                     push_cand(owner && wfilter_pass(f, F, cnt == 1 ? make_sig(j, v.w) : SIG_NONE, v.doc), ent);
                 }
-            } else {
-                // ---- dense overlap: every in-window posting looks its document up in the other runs; the posting of
-                // the lowest run holding the document emits it (entries are flagged: no tag-map twin rule) ----
+            } else if (can_acc) {
+                // ---- dense overlap, narrow window: dense accumulator ----
                 // Candidates listed so far carry tag-map semantics: settle them first.  Documents already emitted by B
-                // for this chunk will be emitted again below; pool_cut() removes the duplicates (same doc ⇒ same exact
-                // score ⇒ adjacent after the sort).
+                // for this chunk are emitted again here; pool_cut() removes the duplicates (same doc ⇒ same exact score
+                // ⇒ adjacent after the sort).
+                flush();
+                dense_query = true;
+                float *acc = (float *)map;
+                const uint32_t span = hi - lo;
+                for (uint32_t i = lane; i < span; i += 32) acc[i] = 0.f;
+                __syncwarp();
+                for (uint32_t j = 0; j < m; ++j) {  // docs are distinct inside a run: no write conflicts
+                    const uint32_t a = __shfl_sync(0xFFFFFFFFu, my_a, j), e = __shfl_sync(0xFFFFFFFFu, my_e, j);
+                    const float s0 = __shfl_sync(0xFFFFFFFFu, w.s0f, j);
+                    for (uint32_t i = a + lane; i < e; i += 32) {
+                        const Posting v = st[i];
+                        acc[v.doc - lo] += score_f32(v.w, s0, s1f);
+                    }
+                    __syncwarp();
+                }
+                for (uint32_t base = 0; base < span; base += 32) {
+                    const uint32_t o = base + lane;
+                    const float F = o < span ? acc[o] : 0.f;
+                    if (__any_sync(0xFFFFFFFFu, F > 0.f && F >= f.Flo)) push_cand(F > 0.f && F >= f.Flo, 0xC0000000u | o);
+                }
+            } else {
+                // ---- dense overlap, wide window (rare): every in-window posting looks its document up in the other
+                // runs; the posting of the lowest run holding the document emits it (no tag-map twin rule) ----
                 flush();
                 for (uint32_t j = 0; j < m; ++j) {
                     const uint32_t a = __shfl_sync(0xFFFFFFFFu, my_a, j), e = __shfl_sync(0xFFFFFFFFu, my_e, j);
