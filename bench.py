@@ -228,14 +228,14 @@ def main():
     torch.cuda.set_stream(stream)
     batch = index.prepare(q_off, q_terms, k)
     # ---- value: prepared batch resident in HBM, kernels only ----
+    sampler = ClockSampler(local_rank)   # started before the warm-up: nvidia-smi needs a moment to come up
+    sampler.start()
     for _ in range(a.warmup):
         batch.run(stream=stream.cuda_stream, timed=False)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
     for _ in range(a.steps):
