@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--k", type=int)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-prune", action="store_true", help="disable MaxScore-style pruning (exhaustive streaming)")
     return ap.parse_args()
 
 
@@ -206,6 +207,8 @@ def main():
         return
 
     info = index.info()
+    if a.no_prune:
+        index.set_option("prune", 0)
 
     cpu_baseline = None
     if rank == 0 and a.gpus == 1 and not a.no_cpu_baseline:
@@ -277,7 +280,12 @@ def main():
     e2e_value = world * nq * e2e_steps / (e2e_ms / 1e3)
     peak, peak_src = hbm_peak()
     kms = statistics.mean(kernel_ms_samples)
-    achieved = st.bytes_algo / (kms / 1e3) / 1e9
+    # algorithmic bytes: 8 B per posting touched + 8 B per result slot + 16 B per query term.  With pruning
+    # only the postings actually streamed count (never more than the exhaustive figure: chunk tails are loaded twice).
+    fetched = int(st.postings_fetched)
+    touched = min(int(st.postings), fetched) if fetched else int(st.postings)
+    bytes_algo = 8 * touched + (int(st.bytes_algo) - 8 * int(st.postings))
+    achieved = bytes_algo / (kms / 1e3) / 1e9
     h2d = 4 * (len(q_off) + len(q_terms) + nq)       # class-grouped ids + offsets + terms
     d2h = nq * k * 8 + nq * 4
     line = {"metric": "queries/sec, 10M-doc synthetic corpus, top-10 (+ achieved HBM GB/s in `roofline`)",
@@ -286,8 +294,10 @@ def main():
             "dtype": "f32 filter + f64 exact re-score (u32 doc ids)", "data": "synthetic", "config": config,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src, "kernel": f"k_search<M={wl['tmax']}>",
-                         "kernel_ms": kms, "algorithmic_bytes_per_launch": int(st.bytes_algo),
-                         "postings_per_launch": int(st.postings)},
+                         "kernel_ms": kms, "algorithmic_bytes_per_launch": bytes_algo,
+                         "postings_exhaustive": int(st.postings), "postings_streamed": fetched,
+                         "pruning": "off" if a.no_prune else "on",
+                         "skipped_frac": max(0.0, 1.0 - touched / max(1, int(st.postings)))},
             "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / e2e_steps, "note": "bm25x_search_batch: host q_off/q_terms in, "

@@ -70,6 +70,7 @@ typedef struct {
     uint64_t bytes_algo;     /* 8 B/posting + 8 B/result slot + 16 B/query term */
     uint32_t launches;       /* kernels launched */
     uint32_t queries;        /* live queries (>= 1 known term) */
+    uint64_t postings_fetched; /* postings actually streamed into shared memory (< postings when pruning bites) */
 } bm25x_search_stats;
 
 /* ---- index lifetime: replaces bm25::build → flush (crates/bm25/src/build.rs:22-71, flush.rs:40-158) for the
@@ -83,7 +84,7 @@ int bm25x_index_get_info(const bm25x_index *idx, bm25x_index_info *out);
  * torch.distributed.broadcast over NVLink).  Sender: bm25x_index_get_layout.  Receiver: bm25x_index_alloc_replica
  * with the sender's layout (scalars only are read), fill the arrays named by its own layout, then
  * bm25x_index_finalize_replica. */
-#define BM25X_N_ARRAYS 11
+#define BM25X_N_ARRAYS 12
 typedef struct {
     uint32_t n_docs, n_terms;
     uint64_t n_postings, n_postings_padded, n_blocks, sum_doc_len;
@@ -95,6 +96,11 @@ typedef struct {
 int bm25x_index_get_layout(const bm25x_index *idx, bm25x_index_layout *out);
 int bm25x_index_alloc_replica(const bm25x_index_layout *like, int device, bm25x_index **out);
 int bm25x_index_finalize_replica(bm25x_index *idx);
+/* Options.  "prune" (default 1): MaxScore-style pruning in the warp-per-query kernel — terms whose summed score upper
+ * bounds (the token-level WAND bound of the reference: TokenTuple.wand_fieldnorm/wand_term_frequency,
+ * flush.rs:101-120, search.rs:363) stay below 5 % of the current k-th score are no longer streamed; their postings
+ * are looked up in HBM only for the candidates.  Results are identical with it on or off. */
+int bm25x_index_set_option(bm25x_index *idx, const char *name, int64_t value);
 /* df of every term (TokenTuple.number_of_documents), host copy. */
 int bm25x_index_get_df(const bm25x_index *idx, uint32_t *df_out);
 

@@ -34,7 +34,7 @@ class IndexInfo(C.Structure):
                 ("device_bytes", C.c_uint64), ("n_blocks", C.c_uint64), ("device", C.c_int)]
 
 
-N_ARRAYS = 11
+N_ARRAYS = 12
 
 
 class IndexLayout(C.Structure):
@@ -46,7 +46,8 @@ class IndexLayout(C.Structure):
 
 class SearchStats(C.Structure):
     _fields_ = [("kernel_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double), ("postings", C.c_uint64),
-                ("bytes_algo", C.c_uint64), ("launches", C.c_uint32), ("queries", C.c_uint32)]
+                ("bytes_algo", C.c_uint64), ("launches", C.c_uint32), ("queries", C.c_uint32),
+                ("postings_fetched", C.c_uint64)]
 
 
 class _Synth(C.Structure):
@@ -87,6 +88,7 @@ def load_library():
     L.bm25x_index_alloc_replica.argtypes = [C.POINTER(IndexLayout), C.c_int, C.POINTER(vp)]
     L.bm25x_index_finalize_replica.argtypes = [vp]
     L.bm25x_index_get_df.argtypes = [vp, u32p]
+    L.bm25x_index_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
     L.bm25x_search_batch.argtypes = [vp, C.c_uint32, u32p, u32p, C.c_uint32, u8p, u32p, f32p, f64p, u16p, u32p,
                                      C.POINTER(SearchStats)]
     L.bm25x_batch_prepare.argtypes = [vp, C.c_uint32, u32p, u32p, C.c_uint32, u8p, C.POINTER(vp)]
@@ -233,6 +235,9 @@ class Index:
 
     def finalize_replica(self):
         _check(load_library().bm25x_index_finalize_replica(self.h))
+
+    def set_option(self, name: str, value: int):
+        _check(load_library().bm25x_index_set_option(self.h, name.encode(), int(value)))
 
     def df(self):
         out = np.zeros(self.n_terms, np.uint32)

@@ -47,6 +47,7 @@ struct DeviceIndex {
     double *s0d = nullptr;          // [n_terms] idf*(k1+1), bm25.rs:348
     double *s1d = nullptr;          // [256] k1*(1-b+b*len(fn)/avgdl), bm25.rs:349-352
     float *s1f = nullptr;           // [256]
+    double *ubd = nullptr;          // [n_terms] upper bound of one posting's exact score (token-level WAND bound)
     uint8_t *fieldnorm = nullptr;   // [n_docs]
     uint16_t *payload = nullptr;    // [n_docs*3]
 };
@@ -62,4 +63,5 @@ struct bm25x_index {
     std::vector<uint8_t> h_keys;       // [n_terms*16] sorted keys (optional)
     cudaStream_t stream = nullptr;
     std::vector<void *> allocs;
+    int prune = 1;                     // MaxScore-style pruning in k_search_wq
 };

@@ -121,6 +121,35 @@ __global__ void k_block_desc(const uint64_t *__restrict__ off_pad, const uint32_
     blk[g] = make_uint2(post[off_pad[lo] + first].doc, post[off_pad[lo] + last - 1].doc);
 }
 
+// Per-term upper bound of a single posting's exact score: max over the term's postings of Cache::evaluate
+// (bm25.rs:355-358) — what the reference stores as the token-level (wand_fieldnorm, wand_term_frequency) arg-max
+// (flush.rs:101-120) and evaluates at query time (search.rs:363).  One block per term; inflated by 2^-40 so that the
+// bound also dominates any later re-association of the f64 sum.
+__global__ void k_term_ub(const uint64_t *__restrict__ off_pad, const uint32_t *__restrict__ df,
+                          const Posting *__restrict__ post, const double *__restrict__ s0d,
+                          const double *__restrict__ s1d, uint32_t n_terms, double *__restrict__ ubd) {
+    __shared__ double red[256];
+    for (uint32_t t = blockIdx.x; t < n_terms; t += gridDim.x) {
+        const Posting *pp = post + off_pad[t];
+        const double s0 = s0d[t];
+        double best = 0.0;
+        for (uint32_t i = threadIdx.x; i < df[t]; i += blockDim.x) {
+            uint32_t w = pp[i].w;
+            double tfd = (double)(w >> 8);
+            double v = __ddiv_rn(__dmul_rn(tfd, s0), __dadd_rn(tfd, s1d[w & 0xFFu]));
+            best = v > best ? v : best;
+        }
+        red[threadIdx.x] = best;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if ((int)threadIdx.x < o && red[threadIdx.x + o] > red[threadIdx.x]) red[threadIdx.x] = red[threadIdx.x + o];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) ubd[t] = red[0] * (1.0 + 9.094947017729282e-13);
+        __syncthreads();
+    }
+}
+
 template <typename T>
 static int dev_alloc(bm25x_index *ix, T **p, size_t n) {
     size_t bytes = sizeof(T) * (n ? n : 1);
@@ -286,6 +315,7 @@ extern "C" int bm25x_index_create(const bm25x_corpus *c, int device, bm25x_index
     TRY(dev_alloc(ix, &d.s0d, T));
     TRY(dev_alloc(ix, &d.s1d, 256));
     TRY(dev_alloc(ix, &d.s1f, 256));
+    TRY(dev_alloc(ix, &d.ubd, T));
     TRY(dev_alloc(ix, &d.fieldnorm, N));
     TRY(dev_alloc(ix, &d.payload, (size_t)N * 3));
     CU(cudaMemcpy(d.post_off, h_off_pad.data(), sizeof(uint64_t) * (T + 1), cudaMemcpyHostToDevice));
@@ -341,6 +371,10 @@ extern "C" int bm25x_index_create(const bm25x_corpus *c, int device, bm25x_index
             k_block_desc<<<(unsigned)((nb + 255) / 256), 256>>>(d.post_off, d.df, d.blk_off, T, nb, d.post, d.blk);
             e = cudaGetLastError();
         }
+        if (e == cudaSuccess && T) {
+            k_term_ub<<<(unsigned)std::min<uint32_t>(T, 148u * 16u), 256>>>(d.post_off, d.df, d.post, d.s0d, d.s1d, T, d.ubd);
+            e = cudaGetLastError();
+        }
         if (e == cudaSuccess) e = cudaDeviceSynchronize();
         cudaFree(d_off);
         cudaFree(d_cdoc);
@@ -385,10 +419,11 @@ extern "C" int bm25x_index_get_info(const bm25x_index *ix, bm25x_index_info *out
 static void layout_arrays(const bm25x_index *ix, void **ptr, uint64_t *bytes) {
     const DeviceIndex &d = ix->d;
     const uint64_t T = d.n_terms, N = d.n_docs;
-    void *p[BM25X_N_ARRAYS] = {d.post, d.post_off, d.df, d.blk_off, d.blk, d.s0f, d.s0d, d.s1d, d.s1f, d.fieldnorm, d.payload};
+    void *p[BM25X_N_ARRAYS] = {d.post, d.post_off, d.df, d.blk_off, d.blk, d.s0f, d.s0d, d.s1d, d.s1f, d.fieldnorm, d.payload,
+                               d.ubd};
     uint64_t b[BM25X_N_ARRAYS] = {sizeof(Posting) * (d.n_post_pad + 2), 8 * (T + 1), 4 * (T ? T : 1), 8 * (T + 1),
                                   8 * (d.n_blocks ? d.n_blocks : 1), 4 * (T ? T : 1), 8 * (T ? T : 1), 8 * 256, 4 * 256,
-                                  N, 6 * N};
+                                  N, 6 * N, 8 * (T ? T : 1)};
     for (int i = 0; i < BM25X_N_ARRAYS; i++) {
         ptr[i] = p[i];
         bytes[i] = b[i];
@@ -462,6 +497,7 @@ extern "C" int bm25x_index_alloc_replica(const bm25x_index_layout *like, int dev
     TRY(dev_alloc(ix, &d.s1f, 256));
     TRY(dev_alloc(ix, &d.fieldnorm, N));
     TRY(dev_alloc(ix, &d.payload, N * 3));
+    TRY(dev_alloc(ix, &d.ubd, T));
     *out = ix;
     return BM25X_OK;
 }
@@ -476,6 +512,19 @@ extern "C" int bm25x_index_finalize_replica(bm25x_index *ix) {
     if (ix->d.n_terms)
         BM25X_CUDA_TRY(cudaMemcpy(ix->h_df.data(), ix->d.df, sizeof(uint32_t) * ix->d.n_terms, cudaMemcpyDeviceToHost));
     return BM25X_OK;
+}
+
+extern "C" int bm25x_index_set_option(bm25x_index *ix, const char *name, int64_t value) {
+    if (!ix || !name) {
+        bm25x_set_error("bm25x_index_set_option: null argument");
+        return BM25X_ERR_INVALID;
+    }
+    if (strcmp(name, "prune") == 0) {
+        ix->prune = value != 0;
+        return BM25X_OK;
+    }
+    bm25x_set_error("bm25x_index_set_option: unknown option '%s'", name);
+    return BM25X_ERR_INVALID;
 }
 
 extern "C" int bm25x_index_get_df(const bm25x_index *ix, uint32_t *df_out) {

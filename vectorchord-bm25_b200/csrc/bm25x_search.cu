@@ -97,6 +97,7 @@ struct bm25x_batch {
     double *d_out_score64 = nullptr;
     uint16_t *d_out_payload = nullptr;
     uint32_t *d_out_n = nullptr;
+    unsigned long long *d_fetched = nullptr;
     uint64_t postings = 0, qterms = 0;
     uint32_t live = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -273,6 +274,7 @@ extern "C" int bm25x_batch_prepare(bm25x_index *ix, uint32_t nq, const uint32_t 
     BTRY(batch_alloc(b, &b->d_out_score64, slots));
     BTRY(batch_alloc(b, &b->d_out_payload, slots * 3));
     BTRY(batch_alloc(b, &b->d_out_n, nq));
+    BTRY(batch_alloc(b, &b->d_fetched, 1));
     e = cudaMemsetAsync(b->d_out_n, 0, 4 * (size_t)(nq ? nq : 1), st);
     if (e == cudaSuccess) e = cudaMemsetAsync(b->d_out_doc, 0xFF, 4 * (slots ? slots : 1), st);
     if (e == cudaSuccess) e = cudaMemsetAsync(b->d_out_score, 0, 4 * (slots ? slots : 1), st);
@@ -301,7 +303,10 @@ extern "C" int bm25x_batch_run(bm25x_batch *b, void *stream_v, bm25x_search_stat
     b->last_stream = (void *)st;
     const DeviceIndex &d = ix->d;
     uint32_t launches = 0;
-    if (stats) BM25X_CUDA_TRY(cudaEventRecord(b->ev0, st));
+    if (stats) {
+        BM25X_CUDA_TRY(cudaMemsetAsync(b->d_fetched, 0, sizeof(unsigned long long), st));
+        BM25X_CUDA_TRY(cudaEventRecord(b->ev0, st));
+    }
     for (int c = 0; c < kNumClasses; ++c) {
         Group &g = b->groups[c];
         if (!g.nq) continue;
@@ -316,6 +321,9 @@ extern "C" int bm25x_batch_run(bm25x_batch *b, void *stream_v, bm25x_search_stat
         sp.s1d = d.s1d;
         sp.s1f = d.s1f;
         sp.payload = d.payload;
+        sp.ubd = d.ubd;
+        sp.prune = ix->prune;
+        sp.fetched = b->d_fetched;
         sp.n_docs = d.n_docs;
         sp.q_ids = g.d_ids;
         sp.q_off = g.d_off;
@@ -363,6 +371,10 @@ extern "C" int bm25x_batch_run(bm25x_batch *b, void *stream_v, bm25x_search_stat
         stats->bytes_algo = 8ull * b->postings + 8ull * (uint64_t)b->live * b->k + 16ull * b->qterms;
         stats->launches = launches;
         stats->queries = b->live;
+        unsigned long long fetched = 0;
+        BM25X_CUDA_TRY(cudaMemcpyAsync(&fetched, b->d_fetched, sizeof(fetched), cudaMemcpyDeviceToHost, st));
+        BM25X_CUDA_TRY(cudaStreamSynchronize(st));
+        stats->postings_fetched = fetched;  // 0 for the CTA kernel (always exhaustive)
     }
     return BM25X_OK;
 }

@@ -84,6 +84,9 @@ struct SearchParams {
     const double *s1d;
     const float *s1f;
     const uint16_t *payload;
+    const double *ubd;                  // per-term upper bound of one posting's exact score
+    unsigned long long *fetched;        // Σ postings actually loaded into shared memory (pruning statistics)
+    int prune;
     uint32_t n_docs;
     // one launch = the queries of one term-count class
     const uint32_t *q_ids;    // original query index

@@ -58,7 +58,10 @@ struct WarpState {
     uint32_t m, dfj, nb, quota_full;
     uint64_t pbase, bbase;
     float s0f;
-    double s0d;
+    double s0d, ubd;
+    // MaxScore pruning (warp-uniform): terms in ne_mask are no longer streamed; ub_ne = Σ of their score bounds
+    uint32_t ne_mask;
+    double ub_ne;
     // chunk planner: gpos = first posting of my term not yet consumed (exact, found by searching the landed chunk)
     uint32_t gpos, lo, chunk;
 };
@@ -69,7 +72,7 @@ struct WarpState {
 // Called as soon as gpos is known, so that the round trip hides behind the processing of the current chunk.
 template <class C>
 __device__ __forceinline__ uint32_t plan_prefetch(const SearchParams &p, const WarpState<C> &w, int lane) {
-    const bool act = lane < (int)w.m && w.gpos < w.dfj;
+    const bool act = lane < (int)w.m && w.gpos < w.dfj && !((w.ne_mask >> lane) & 1u);
     const uint32_t quota = act ? (w.chunk < 2 ? 1u : w.quota_full) : 0u;
     const uint32_t ib = w.gpos / BM25X_BLOCK;
     uint32_t prop = INF;
@@ -79,7 +82,7 @@ __device__ __forceinline__ uint32_t plan_prefetch(const SearchParams &p, const W
 
 template <class C>
 __device__ __forceinline__ ChunkPlan plan_chunk(const SearchParams &p, WarpState<C> &w, int lane, uint32_t prop) {
-    const bool act = lane < (int)w.m && w.gpos < w.dfj;
+    const bool act = lane < (int)w.m && w.gpos < w.dfj && !((w.ne_mask >> lane) & 1u);
     const uint32_t quota = act ? (w.chunk < 2 ? 1u : w.quota_full) : 0u;
     const uint32_t ib = w.gpos / BM25X_BLOCK;
     // window end: the smallest "first doc of the block just past my quota" over the terms
@@ -119,6 +122,30 @@ __device__ __forceinline__ void issue_chunk(const SearchParams &p, const WarpSta
     if (c.len > 0)
         tma_load_1d(stage + (size_t)c.off * sizeof(Posting), p.post + w.pbase + c.gsrc, c.len * (uint32_t)sizeof(Posting),
                     bar);
+}
+
+// Posting word of `doc` in a term that is not streamed any more (non-essential): block table first
+// (SummaryTuple.{min,max}_document_id), then inside the 128-posting block.  ~24 dependent L2 reads; candidates only.
+__device__ __forceinline__ uint32_t probe_global(const SearchParams &p, uint64_t pbase, uint64_t bbase, uint32_t nb,
+                                                 uint32_t dfj, uint32_t doc) {
+    uint32_t l = 0, r = nb;  // first block whose first doc is > doc
+    while (l < r) {
+        uint32_t mid = (l + r) >> 1;
+        if (__ldg(&p.blk[bbase + mid].x) <= doc) l = mid + 1;
+        else r = mid;
+    }
+    if (l == 0) return 0u;
+    const uint32_t s = (l - 1) * BM25X_BLOCK, e = min(s + BM25X_BLOCK, dfj);
+    const Posting *pp = p.post + pbase;
+    l = s;
+    r = e;
+    while (l < r) {
+        uint32_t mid = (l + r) >> 1;
+        if (__ldg(&pp[mid].doc) < doc) l = mid + 1;
+        else r = mid;
+    }
+    if (l < e && __ldg(&pp[l].doc) == doc) return __ldg(&pp[l].w);
+    return 0u;
 }
 
 // Warp-private pool: (score bits, doc, signature), unsorted until pool_cut.
@@ -215,6 +242,10 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_wq(const __grid_consta
         w.pbase = w.bbase = 0;
         w.s0f = 0.f;
         w.s0d = 0.0;
+        w.ubd = 0.0;
+        w.ne_mask = 0u;
+        w.ub_ne = 0.0;
+        unsigned long long fetched = 0;
         if (lane < (int)w.m) {
             uint32_t term = p.q_terms[t0 + lane];
             w.dfj = p.df[term];
@@ -223,6 +254,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_wq(const __grid_consta
             w.nb = (w.dfj + BM25X_BLOCK - 1) / BM25X_BLOCK;
             w.s0f = p.s0f[term];
             w.s0d = p.s0d[term];
+            w.ubd = p.ubd[term];
         }
         {
             uint64_t sumdf = w.dfj;
@@ -286,7 +318,29 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_wq(const __grid_consta
                 f.dk = pl.d[k - 1];
                 f.tie_sig = pl.g[k - 1];
                 f.tie_dk = f.tie_sig != SIG_NONE ? f.dk : INF;
-                const double flo = f.Sk * (1.0 - kEps);
+                // MaxScore: move the terms with the smallest score bounds out of the streamed set while the sum of
+                // their bounds stays below 5 % of the k-th score (a document holding only such terms cannot enter; for
+                // the others the bound is added back in the filter and the exact contribution is probed in phase D)
+                if (p.prune) {
+                    for (;;) {
+                        const bool ess = lane < (int)m && !((w.ne_mask >> lane) & 1u);
+                        unsigned long long key = ess ? (unsigned long long)__double_as_longlong(w.ubd) : ~0ull;
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            unsigned long long other = __shfl_xor_sync(0xFFFFFFFFu, key, o);
+                            key = other < key ? other : key;
+                        }
+                        const uint32_t who = __ballot_sync(0xFFFFFFFFu, ess && (unsigned long long)__double_as_longlong(w.ubd) == key);
+                        const uint32_t ness = __popc(__ballot_sync(0xFFFFFFFFu, ess));
+                        if (who == 0u || ness <= 1u) break;
+                        const double ub = __longlong_as_double((long long)key);
+                        if (!(w.ub_ne + ub <= 0.05 * f.Sk)) break;
+                        w.ne_mask |= 1u << (__ffs(who) - 1);
+                        w.ub_ne += ub;
+                    }
+                    if (w.ne_mask) f.tie_dk = INF;  // a single-term document may hold non-streamed terms: no tie shortcut
+                }
+                const double flo = f.Sk * (1.0 - kEps) - w.ub_ne;
                 f.Flo = __double2float_rd(flo);
                 // F = s0·tf/(tf+s1) >= flo  ⇔  tf >= flo/(s0-flo)·s1  (s0 > flo), never when s0 <= flo.  Solved in f64
                 // from the exact s0 (no cancellation trouble), shrunk by 2^-20 to stay conservative in f32.
@@ -306,6 +360,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_wq(const __grid_consta
             parbits ^= 1u << stage;
             const Posting *st = (const Posting *)(ws + C::off_stage + C::stage_bytes * stage);
             const uint32_t lo = cur.lo, hi = cur.hi;
+            fetched += cur.len;
             // exact in-window range of my run (lane < m): [my_a, my_e) — one binary search for the window end; the
             // load started at most one posting before the window start
             uint32_t my_a = cur.off, my_e = cur.off;
@@ -343,22 +398,33 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_wq(const __grid_consta
                     // bits 31+30 set: document given as offset from the window start (dense accumulator path)
                     const uint32_t doc = (ent >> 30) == 3u ? lo + (ent & 0x3FFFFFFFu) : st[ent & 0xFFFFu].doc;
                     double Sx = 0.0;
-                    uint32_t cnt = 0, sig = SIG_NONE;
+                    uint32_t cnt = 0, cnt_streamed = 0, sig = SIG_NONE;
                     for (uint32_t jj = 0; jj < m; ++jj) {
                         const uint32_t a = __shfl_sync(0xFFFFFFFFu, my_a, jj), e = __shfl_sync(0xFFFFFFFFu, my_e, jj);
                         const double s0d = __shfl_sync(0xFFFFFFFFu, w.s0d, jj);
+                        const bool ne = (w.ne_mask >> jj) & 1u;  // not streamed: look the posting up in HBM
+                        uint64_t pb = 0, bb = 0;
+                        uint32_t nbj = 0, dfq = 0;
+                        if (ne) {
+                            pb = __shfl_sync(0xFFFFFFFFu, w.pbase, jj);
+                            bb = __shfl_sync(0xFFFFFFFFu, w.bbase, jj);
+                            nbj = __shfl_sync(0xFFFFFFFFu, w.nb, jj);
+                            dfq = __shfl_sync(0xFFFFFFFFu, w.dfj, jj);
+                        }
                         if (!has) continue;
-                        const uint32_t wv = find_in(st, a, e, doc);
+                        const uint32_t wv = ne ? probe_global(p, pb, bb, nbj, dfq, doc) : find_in(st, a, e, doc);
                         if (wv) {
                             Sx = __dadd_rn(Sx, score_f64(wv, s0d, p.s1d));
                             cnt++;
+                            cnt_streamed += ne ? 0u : 1u;
                             sig = make_sig(jj, wv);
                         }
                     }
                     bool keep = has;
                     if (keep && p.allow && !((p.allow[doc >> 3] >> (doc & 7u)) & 1u)) keep = false;
                     // a posting whose tag won its slot although other runs hold the document: its twin carries it
-                    if (keep && cnt > 1 && (ent >> 31) == 0 &&
+                    // (only runs that are streamed take part in the tag map: probed terms do not make a twin)
+                    if (keep && cnt_streamed > 1 && (ent >> 31) == 0 &&
                         map[slot_of<C::LOG_S>(doc)] == (uint8_t)(((ent >> 16) & 0x7FFFu) + 1u))
                         keep = false;
                     keep = keep && (!f.tv || Sx > f.Sk || (Sx == f.Sk && doc < f.dk));
@@ -590,6 +656,11 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_wq(const __grid_consta
             }
         }
         if (lane == 0) p.out_n[qid] = (uint32_t)pn;
+        if (p.fetched) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) fetched += __shfl_xor_sync(0xFFFFFFFFu, fetched, o);
+            if (lane == 0) atomicAdd(p.fetched, fetched);
+        }
         __syncwarp();
     }
 }
