@@ -32,8 +32,8 @@ WORKLOADS = {
                seed=0xB25C0DE0 + 2, desc="C2: 1M docs, vocab 30k, 64 terms/doc, 10k 1-term queries"),
     "c1": dict(docs=1_000, vocab=1_000, doclen=32, queries=100, tmin=3, tmax=3, zipf=0.0, k=10,
                seed=0xB25C0DE0 + 1, desc="C1: 1k docs, 100 3-term queries"),
-    "c4": dict(docs=10_000_000, vocab=100_000, doclen=128, queries=1_000, tmin=8, tmax=8, zipf=1.0, k=10,
-               seed=0xB25C0DE0 + 4, desc="C4: 10M docs Zipf(1), 8-term queries, exhaustive (1000-query subset)"),
+    "c4": dict(docs=10_000_000, vocab=100_000, doclen=128, queries=4_000, tmin=8, tmax=8, zipf=1.0, k=10,
+               seed=0xB25C0DE0 + 4, desc="C4: 10M docs Zipf(1), 8-term queries (4000-query subset; --no-prune = exhaustive)"),
     "c5": dict(docs=50_000_000, vocab=100_000, doclen=128, queries=100_000, tmin=1, tmax=8, zipf=0.0, k=10,
                seed=0xB25C0DE0 + 5, desc="C5: 50M docs, mixed 1-8 term queries (per-GPU shard of the 1M batch)"),
 }

@@ -112,6 +112,25 @@ def test_prefilter_bitmap(m, orc):
     ix.close()
 
 
+def test_pruning_on_off_identical(m, orc):
+    """MaxScore-style pruning (non-streamed head terms, HBM probes for candidates) must not change a single bit of the
+    result; with Zipf head terms in most queries it must also stream fewer postings than the exhaustive run."""
+    c = m.synth_corpus(71, 60000, 3000, 24, 96, 1.0)
+    q_off, q_terms = m.synth_queries(72, 200, 3000, 2, 8, c.post_off, 1.0)
+    ix = m.Index.from_corpus(c)
+    oix = _oracle_index(orc, c)
+    on = ix.search_batch(q_off, q_terms, 10)
+    ix.set_option("prune", 0)
+    off = ix.search_batch(q_off, q_terms, 10)
+    for key in ("doc", "score", "score64", "n"):
+        assert np.array_equal(on[key], off[key]), key
+    _compare(on, oix, q_off, q_terms, 10, what="prune")
+    assert 0 < on["stats"].postings_fetched < off["stats"].postings_fetched
+    with pytest.raises(m.Bm25xError):
+        ix.set_option("no-such-option", 1)
+    ix.close()
+
+
 def test_evaluate_matches_oracle_bitwise(m, orc):
     c = m.synth_corpus(51, 5000, 400, 2, 120, 0.8)
     ix = m.Index.from_corpus(c)

@@ -20,7 +20,7 @@ struct WCfg {
     static constexpr int M = M_;                    // max live terms (lanes 0..M-1 own the terms)
     static constexpr int KP = KP_;                  // pool capacity (power of two >= k + LCAP)
     // block budget per chunk (Σ quota = CB exactly): two 128-posting blocks per term for m = M <= 4
-    static constexpr int CB = M_ <= 4 ? 2 * M_ : M_;
+    static constexpr int CB = M_ <= 4 ? 2 * M_ : M_;  // (8-term class: one block per term keeps the chunk within reach of the 4 KiB tag map)
     static constexpr int NSTG = 1;                  // stages per warp: 1 = rely on the other warps to hide the load latency
     static constexpr int LOG_S = 12;                // tag map slots (bytes)
     static constexpr int LCAP = 64;                 // candidate / possible-duplicate list entries
@@ -62,8 +62,9 @@ struct WarpState {
     // MaxScore pruning (warp-uniform): terms in ne_mask are no longer streamed; ub_ne = Σ of their score bounds
     uint32_t ne_mask;
     double ub_ne;
-    // chunk planner: gpos = first posting of my term not yet consumed (exact, found by searching the landed chunk)
-    uint32_t gpos, lo, chunk;
+    // chunk planner: gpos = first posting of my term not yet consumed (exact, found by searching the landed chunk);
+    // next_doc = its doc id when it has already been seen in shared memory (0 = unknown)
+    uint32_t gpos, next_doc, lo, chunk;
 };
 
 // Plans the next chunk.  Loads start at the exact posting where the previous window ended (rounded down to the
@@ -91,7 +92,9 @@ __device__ __forceinline__ ChunkPlan plan_chunk(const SearchParams &p, WarpState
     ChunkPlan c;
     c.len = 0;
     c.gsrc = w.gpos & ~1u;
-    if (act) {
+    // a term whose next posting is known to lie at or past the window end has nothing in this chunk: do not load it
+    // again (sparse terms next to dense ones would otherwise re-load the same block for thousands of chunks)
+    if (act && !(hi != INF && w.next_doc >= hi)) {
         uint32_t endp = min((ib + quota) * BM25X_BLOCK, w.dfj);
         c.len = (endp - c.gsrc + 1u) & ~1u;  // whole 16-byte units; an odd tail is the term's pad slot
     }
@@ -267,6 +270,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_wq(const __grid_consta
             w.quota_full = lane < (int)w.m ? 1u + share + (lane < (int)left ? 1u : 0u) : 0u;
         }
         w.gpos = 0;
+        w.next_doc = 0;
         w.lo = 0;
         w.chunk = 0;
         const uint32_t m = w.m;
@@ -374,6 +378,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_wq(const __grid_consta
                 }
                 my_e = l;
                 w.gpos = cur.gsrc + (my_e - cur.off);  // first posting of my term at or past the window end
+                w.next_doc = my_e < cur.off + cur.len ? st[my_e].doc : 0u;
             }
             // ---- prefetch: plan + issue the next chunk into the other stage (overlaps the processing below) ----
             ChunkPlan nxt;
