@@ -92,6 +92,18 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def measured_traffic(workload, nq, k):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the search kernel from the committed `ncu --set full` capture
+    of this exact launch (profiles/r1_final_traffic.json), else None."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r1_final_traffic.json")))
+        if t["workload"] == workload and t["queries"] == nq and t["k"] == k:
+            return t["dram_bytes_read"] + t["dram_bytes_write"]
+    except Exception:
+        pass
+    return None
+
+
 def hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -293,7 +305,7 @@ def main():
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 filter + f64 exact re-score (u32 doc ids)", "data": "synthetic", "config": config,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": f"k_search<M={wl['tmax']}>",
+                         "traffic": None if a.no_prune else measured_traffic(a.workload, nq, k), "peak_source": peak_src, "kernel": f"k_search<M={wl['tmax']}>",
                          "kernel_ms": kms, "algorithmic_bytes_per_launch": bytes_algo,
                          "postings_exhaustive": int(st.postings), "postings_streamed": fetched,
                          "pruning": "off" if a.no_prune else "on",
