@@ -183,3 +183,26 @@ def test_config2_sample_1M_docs(m, orc):
     sub = {k: (v[idx] if isinstance(v, np.ndarray) else v) for k, v in res.items()}
     _compare(sub, oix, sub_off, q_terms[idx], 10, what="C2")
     ix.close()
+
+
+def test_config3_sample_10M_docs(m, orc):
+    """BASELINE config 3 shape at full size (10M docs, vocab 100k, 128 terms/doc): 3-term queries top-10 on the GPU;
+    every query checked for the size-independent properties, a sample checked bit for bit against the oracle."""
+    c = m.synth_corpus(0xB25C0DE3, 10_000_000, 100_000, 128)
+    q_off, q_terms = m.synth_queries(0xB25C0DE3 + 1000, 4000, 100_000, 3, 3, c.post_off)
+    ix = m.Index.from_corpus(c)
+    res = ix.search_batch(q_off, q_terms, 10)
+    assert np.all(res["n"] == 10)
+    s = res["score64"]
+    assert np.all(s[:, :-1] >= s[:, 1:])
+    tie = s[:, :-1] == s[:, 1:]
+    assert np.all(res["doc"][:, :-1][tie] < res["doc"][:, 1:][tie])
+    assert np.all(res["doc"] < 10_000_000)
+    assert all(len(set(r)) == 10 for r in res["doc"][::50].tolist())            # no document twice
+    oix = _oracle_index(orc, c)
+    idx = np.arange(0, 4000, 211)
+    sub_off = (3 * np.arange(len(idx) + 1)).astype(np.uint32)
+    sub_terms = np.concatenate([q_terms[q_off[i]:q_off[i + 1]] for i in idx])
+    sub = {k: (v[idx] if isinstance(v, np.ndarray) else v) for k, v in res.items()}
+    _compare(sub, oix, sub_off, sub_terms, 10, what="C3")
+    ix.close()

@@ -461,8 +461,9 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_wq(const __grid_consta
             constexpr uint32_t ACC_DOCS = (1u << C::LOG_S) / 4u;
             const bool can_acc = hi - lo <= ACC_DOCS;
             bool dense = dense_query && can_acc;  // the previous chunk was dense: skip the tag-map phases right away
-            // ---- A: mark ----
-            if (!dense) {
+            // ---- A: mark (a single-term query has nothing to unite: no tag map at all) ----
+            const bool multi = m > 1;
+            if (!dense && multi) {
                 for (uint32_t j = 0; j < m; ++j) {
                     const uint32_t a = __shfl_sync(0xFFFFFFFFu, my_a, j), e = __shfl_sync(0xFFFFFFFFu, my_e, j);
                     const uint8_t tagv = (uint8_t)(j + 1);
@@ -479,7 +480,11 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_wq(const __grid_consta
                     const uint32_t i0 = base + lane, i1 = i0 + 32;
                     const bool v0 = i0 < e, v1 = i1 < e;
                     const Posting p0 = st[v0 ? i0 : a], p1 = st[v1 ? i1 : a];
-                    const uint8_t t0 = map[slot_of<C::LOG_S>(p0.doc)], t1 = map[slot_of<C::LOG_S>(p1.doc)];
+                    uint8_t t0 = tagv, t1 = tagv;
+                    if (multi) {
+                        t0 = map[slot_of<C::LOG_S>(p0.doc)];
+                        t1 = map[slot_of<C::LOG_S>(p1.doc)];
+                    }
                     const bool d0 = v0 && t0 != tagv, d1 = v1 && t1 != tagv;
                     // threshold test in the tf domain (no division); signature tie rule as in wfilter_pass
                     const bool g0 = (float)(p0.w >> 8) >= ctf * s1f[p0.w & 0xFFu];
@@ -624,7 +629,8 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_wq(const __grid_consta
             if (nc) flush();
             // zero the tag map for the next chunk
             __syncwarp();
-            for (int i = lane; i < (1 << C::LOG_S) / 16; i += 32) ((uint4 *)map)[i] = make_uint4(0, 0, 0, 0);
+            if (multi)
+                for (int i = lane; i < (1 << C::LOG_S) / 16; i += 32) ((uint4 *)map)[i] = make_uint4(0, 0, 0, 0);
             __syncwarp();
             if (!have_next) break;
             if (C::NSTG == 1) {  // single-buffered: the stage is free again only now
