@@ -20,7 +20,8 @@ struct WCfg {
     static constexpr int M = M_;                    // max live terms (lanes 0..M-1 own the terms)
     static constexpr int KP = KP_;                  // pool capacity (power of two >= k + LCAP)
     // block budget per chunk (Σ quota = CB exactly): two 128-posting blocks per term for m = M <= 4
-    static constexpr int CB = M_ <= 4 ? 2 * M_ : M_;  // (8-term class: one block per term keeps the chunk within reach of the 4 KiB tag map)
+    static constexpr int CB = 2 * M_;
+    static constexpr int SUB_TARGET = 640;          // postings per tag-map sub-window (classes with more than 4 terms)
     static constexpr int NSTG = 1;                  // stages per warp: 1 = rely on the other warps to hide the load latency
     static constexpr int LOG_S = 12;                // tag map slots (bytes)
     static constexpr int LCAP = 64;                 // candidate / possible-duplicate list entries
@@ -363,22 +364,22 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_wq(const __grid_consta
             mbar_wait(&bars[stage], (parbits >> stage) & 1u);
             parbits ^= 1u << stage;
             const Posting *st = (const Posting *)(ws + C::off_stage + C::stage_bytes * stage);
-            const uint32_t lo = cur.lo, hi = cur.hi;
+            const uint32_t clo = cur.lo, chi = cur.hi;
             fetched += cur.len;
-            // exact in-window range of my run (lane < m): [my_a, my_e) — one binary search for the window end; the
+            // exact in-window range of my run (lane < m): [run_a, run_e) — one binary search for the window end; the
             // load started at most one posting before the window start
-            uint32_t my_a = cur.off, my_e = cur.off;
+            uint32_t run_a = cur.off, run_e = cur.off;
             if (cur.len > 0) {
-                if (st[my_a].doc < lo) my_a++;
-                uint32_t l = my_a, r = cur.off + cur.len;
+                if (st[run_a].doc < clo) run_a++;
+                uint32_t l = run_a, r = cur.off + cur.len;
                 while (l < r) {
                     uint32_t mid = (l + r) >> 1;
-                    if (st[mid].doc < hi) l = mid + 1;
+                    if (st[mid].doc < chi) l = mid + 1;
                     else r = mid;
                 }
-                my_e = l;
-                w.gpos = cur.gsrc + (my_e - cur.off);  // first posting of my term at or past the window end
-                w.next_doc = my_e < cur.off + cur.len ? st[my_e].doc : 0u;
+                run_e = l;
+                w.gpos = cur.gsrc + (run_e - cur.off);  // first posting of my term at or past the window end
+                w.next_doc = run_e < cur.off + cur.len ? st[run_e].doc : 0u;
             }
             // ---- prefetch: plan + issue the next chunk into the other stage (overlaps the processing below) ----
             ChunkPlan nxt;
@@ -393,6 +394,30 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_wq(const __grid_consta
                 issue_chunk<C>(p, w, nxt, ws + C::off_stage + C::stage_bytes * (stage ^ 1), &bars[stage ^ 1], lane);
             }
 
+            // The chunk is processed in doc sub-windows of at most ~SUB_TARGET postings: loads can be large while the
+            // tag map only ever has to unite a few hundred postings.
+            // (classes up to 4 terms load two blocks per term: one sub-window, resolved at compile time)
+            uint32_t nsub = 1u;
+            if (C::M > 4) {
+                const uint32_t chunk_postings = __reduce_add_sync(0xFFFFFFFFu, run_e - run_a);
+                nsub = max(1u, (chunk_postings + C::SUB_TARGET - 1) / C::SUB_TARGET);
+            }
+            uint32_t sub_next = run_a;
+            for (uint32_t sub = 0; sub < nsub; ++sub) {
+            const uint32_t lo = clo + (uint32_t)(((uint64_t)(chi - clo) * sub) / nsub);
+            const uint32_t hi = sub + 1 == nsub ? chi : clo + (uint32_t)(((uint64_t)(chi - clo) * (sub + 1)) / nsub);
+            const uint32_t my_a = sub_next;
+            uint32_t my_e = run_e;
+            if (sub + 1 < nsub) {  // my run's end inside this sub-window
+                uint32_t l = my_a, r = run_e;
+                while (l < r) {
+                    uint32_t mid = (l + r) >> 1;
+                    if (st[mid].doc < hi) l = mid + 1;
+                    else r = mid;
+                }
+                my_e = l;
+            }
+            sub_next = my_e;
             uint32_t nd = 0, nc = 0;  // list lengths (warp-uniform)
             // exact re-score of the listed candidates → pool
             auto flush = [&]() {
@@ -632,6 +657,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_wq(const __grid_consta
             if (multi)
                 for (int i = lane; i < (1 << C::LOG_S) / 16; i += 32) ((uint4 *)map)[i] = make_uint4(0, 0, 0, 0);
             __syncwarp();
+            }  // sub-windows
             if (!have_next) break;
             if (C::NSTG == 1) {  // single-buffered: the stage is free again only now
                 nxt = plan_chunk<C>(p, w, lane, prop_next);
