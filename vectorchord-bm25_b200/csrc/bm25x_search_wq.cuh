@@ -208,7 +208,6 @@ __device__ __forceinline__ bool wfilter_pass(const WFilter &f, float F, uint32_t
 template <class C>
 __global__ void __launch_bounds__(C::THREADS, 1) k_search_wq(const __grid_constant__ SearchParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
-    constexpr int M = C::M;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
     float *s1f = (float *)(smem + C::off_s1f);
