@@ -113,6 +113,18 @@ int orc_synth_doc(uint64_t seed, uint32_t doc, uint32_t vocab, uint32_t len_min,
                   uint32_t len_max, const uint64_t *zipf_thr, uint32_t *terms_out,
                   uint32_t *tfs_out, uint32_t *len_out);
 
+/* ---- posting-block codec (bm25_codec.c): compression.rs:36-136 + crates/simd bit/byte packing ---- */
+uint32_t orc_compress_document_ids(uint32_t min_doc, const uint32_t *docs, uint32_t n, uint8_t *meta, uint8_t *out);
+uint32_t orc_decompress_document_ids(uint32_t min_doc, uint8_t meta, const uint8_t *in, uint32_t n_bytes,
+                                     uint32_t *docs);
+uint32_t orc_compress_term_frequencies(const uint32_t *tfs, uint32_t n, uint8_t *meta, uint8_t *out);
+uint32_t orc_decompress_term_frequencies(uint8_t meta, const uint8_t *in, uint32_t n_bytes, uint32_t *tfs);
+/* flush.rs:78-120 over a CSR corpus: two passes (bytes == NULL → sizes only); returns the payload size */
+uint64_t orc_encode_blocks(uint32_t n_terms, const uint64_t *post_off, const uint32_t *post_doc,
+                           const uint32_t *post_tf, uint64_t *term_blk_off, uint32_t *blk_min, uint32_t *blk_n,
+                           uint8_t *meta_doc, uint8_t *meta_tf, uint64_t *doc_off, uint64_t *tf_off,
+                           uint8_t *bytes);
+
 #ifdef __cplusplus
 }
 #endif

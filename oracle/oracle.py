@@ -18,8 +18,8 @@ _SO = os.path.join(_HERE, "libbm25_oracle.so")
 
 def build(force: bool = False) -> str:
     """Compile the oracle with the committed Makefile (gcc, seconds)."""
-    src = os.path.join(_HERE, "bm25_oracle.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("bm25_oracle.c", "bm25_codec.c", "bm25_oracle.h")]
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return _SO
 
@@ -90,6 +90,16 @@ def lib():
     L.orc_draw_term.argtypes = [C.c_uint64, C.c_uint32, u64p]
     L.orc_synth_doc.restype = C.c_int
     L.orc_synth_doc.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, u64p, u32p, u32p, u32p]
+    L.orc_compress_document_ids.restype = C.c_uint32
+    L.orc_compress_document_ids.argtypes = [C.c_uint32, u32p, C.c_uint32, u8p, u8p]
+    L.orc_decompress_document_ids.restype = C.c_uint32
+    L.orc_decompress_document_ids.argtypes = [C.c_uint32, C.c_uint8, u8p, C.c_uint32, u32p]
+    L.orc_compress_term_frequencies.restype = C.c_uint32
+    L.orc_compress_term_frequencies.argtypes = [u32p, C.c_uint32, u8p, u8p]
+    L.orc_decompress_term_frequencies.restype = C.c_uint32
+    L.orc_decompress_term_frequencies.argtypes = [C.c_uint8, u8p, C.c_uint32, u32p]
+    L.orc_encode_blocks.restype = C.c_uint64
+    L.orc_encode_blocks.argtypes = [C.c_uint32, u64p, u32p, u32p, u64p, u32p, u32p, u8p, u8p, u64p, u64p, u8p]
     _lib = L
     return L
 
@@ -261,3 +271,66 @@ def gen_queries(seed, nq, vocab, nterms_min, nterms_max, df_of, zipf_s=0.0):
         out.extend(got)
         off.append(len(out))
     return np.array(off, dtype=np.uint32), np.array(out, dtype=np.uint32)
+
+
+# ---- posting-block codec (bm25_codec.c; compression.rs:36-136) ----
+
+def compress_document_ids(min_doc, docs):
+    """-> (metadata byte, payload bytes)   (compression.rs:36-63)"""
+    docs = np.ascontiguousarray(docs, dtype=np.uint32)
+    out = np.zeros(512, dtype=np.uint8)
+    meta = C.c_uint8(0)
+    n = lib().orc_compress_document_ids(int(min_doc), _p(docs, C.c_uint32), len(docs), C.byref(meta), _p(out, C.c_uint8))
+    return meta.value, out[:n].copy()
+
+
+def decompress_document_ids(min_doc, meta, payload):
+    """-> doc ids, or None when the block is malformed   (compression.rs:65-94)"""
+    payload = np.ascontiguousarray(payload, dtype=np.uint8)
+    out = np.zeros(128, dtype=np.uint32)
+    n = lib().orc_decompress_document_ids(int(min_doc), int(meta), _p(payload, C.c_uint8), len(payload), _p(out, C.c_uint32))
+    return None if n == 0xFFFFFFFF else out[:n].copy()
+
+
+def compress_term_frequencies(tfs):
+    tfs = np.ascontiguousarray(tfs, dtype=np.uint32)
+    out = np.zeros(512, dtype=np.uint8)
+    meta = C.c_uint8(0)
+    n = lib().orc_compress_term_frequencies(_p(tfs, C.c_uint32), len(tfs), C.byref(meta), _p(out, C.c_uint8))
+    return meta.value, out[:n].copy()
+
+
+def decompress_term_frequencies(meta, payload):
+    payload = np.ascontiguousarray(payload, dtype=np.uint8)
+    out = np.zeros(128, dtype=np.uint32)
+    n = lib().orc_decompress_term_frequencies(int(meta), _p(payload, C.c_uint8), len(payload), _p(out, C.c_uint32))
+    return None if n == 0xFFFFFFFF else out[:n].copy()
+
+
+class EncodedBlocks:
+    """A corpus' postings as the reference's sealed segment stores them: blocks of 128 in the block codec
+    (flush.rs:78-120).  Arrays are what bm25x_index_create_from_blocks takes."""
+
+    def __init__(self, corpus: "Corpus"):
+        L = lib()
+        T = corpus.n_terms
+        off = corpus.post_off
+        df = (off[1:] - off[:-1]).astype(np.uint64)
+        nb = int(((df + 127) // 128).sum())
+        self.corpus = corpus
+        self.term_blk_off = np.zeros(T + 1, dtype=np.uint64)
+        args = (T, _p(off, C.c_uint64), _p(corpus.post_doc, C.c_uint32), _p(corpus.post_tf, C.c_uint32))
+        n_bytes = L.orc_encode_blocks(*args, _p(self.term_blk_off, C.c_uint64), None, None, None, None, None, None, None)
+        self.blk_min = np.zeros(max(nb, 1), dtype=np.uint32)
+        self.blk_n = np.zeros(max(nb, 1), dtype=np.uint32)
+        self.meta_doc = np.zeros(max(nb, 1), dtype=np.uint8)
+        self.meta_tf = np.zeros(max(nb, 1), dtype=np.uint8)
+        self.doc_off = np.zeros(max(nb, 1), dtype=np.uint64)
+        self.tf_off = np.zeros(max(nb, 1), dtype=np.uint64)
+        self.bytes = np.zeros(max(int(n_bytes), 1), dtype=np.uint8)
+        got = L.orc_encode_blocks(*args, _p(self.term_blk_off, C.c_uint64), _p(self.blk_min, C.c_uint32), _p(self.blk_n, C.c_uint32),
+                                  _p(self.meta_doc, C.c_uint8), _p(self.meta_tf, C.c_uint8),
+                                  _p(self.doc_off, C.c_uint64), _p(self.tf_off, C.c_uint64), _p(self.bytes, C.c_uint8))
+        assert got == n_bytes and int(self.term_blk_off[T]) == nb
+        self.n_blocks = nb
+        self.n_bytes = int(n_bytes)
