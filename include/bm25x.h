@@ -79,6 +79,35 @@ int bm25x_index_create(const bm25x_corpus *corpus, int device, bm25x_index **out
 void bm25x_index_destroy(bm25x_index *idx);
 int bm25x_index_get_info(const bm25x_index *idx, bm25x_index_info *out);
 
+/* ---- the sealed segment AS STORED by the reference (ingest of the on-page format).  While walking the
+ * index pages the caller flattens, per token, the chain of SummaryTuples (crates/bm25/src/tuples.rs:900-910) and the
+ * BlockTuples they point to (tuples.rs:973-983) that flush() wrote (flush.rs:78-120); the block payloads are taken
+ * exactly as compression.rs:36-136 left them (4-lane vertical bit packing with delta-coded doc ids for full blocks,
+ * byte packing for a token's last block) and are decoded on the GPU — replacing fill_block (search.rs:498-518) +
+ * crates/simd/src/bitpacking*.rs / bytepacking*.rs on the CPU.  Searches on the resulting index are identical to those
+ * on an index created from the same postings with bm25x_index_create. */
+typedef struct {
+    uint32_t n_docs;
+    const uint32_t *doc_len;       /* [n_docs] exact lengths, or NULL: then the two fields below (what the pages hold) */
+    const uint8_t *doc_fieldnorm;  /* [n_docs] DocumentTuple.fieldnorm (tuples.rs:756-762); used when doc_len == NULL */
+    uint64_t sum_doc_len;          /* JumpTuple.sum_of_document_lengths (tuples.rs:141-160); used when doc_len == NULL */
+    const uint16_t *payload;       /* [n_docs*3] DocumentTuple.payload (ctid), or NULL */
+    uint32_t n_terms;
+    const uint8_t *term_key;       /* [n_terms*16] TokenTuple.id, strictly ascending, or NULL */
+    const uint64_t *term_blk_off;  /* [n_terms+1] first block of each token; term_blk_off[n_terms] == n_blocks */
+    uint64_t n_blocks;
+    const uint32_t *blk_min_doc;   /* [n_blocks] SummaryTuple.min_document_id: the delta seed of the block */
+    const uint32_t *blk_n;         /* [n_blocks] SummaryTuple.number_of_documents: 128 except a token's last block */
+    const uint8_t *blk_meta_doc;   /* [n_blocks] BlockTuple.metadata_document_ids: flag << 7 | width */
+    const uint8_t *blk_meta_tf;    /* [n_blocks] BlockTuple.metadata_term_frequencies */
+    const uint64_t *blk_doc_off;   /* [n_blocks] byte offset of compressed_document_ids inside `bytes` */
+    const uint64_t *blk_tf_off;    /* [n_blocks] byte offset of compressed_term_frequencies inside `bytes` */
+    const uint8_t *bytes;          /* concatenated block payloads */
+    uint64_t n_bytes;
+    double k1, b;
+} bm25x_blocks;
+int bm25x_index_create_from_blocks(const bm25x_blocks *blocks, int device, bm25x_index **out);
+
 /* ---- replication across the GPUs of one box (queries shard, the index is replicated; NCCL broadcast at load
  * only).  The library stays NCCL-free: it exposes the device arrays, the caller moves the bytes (bench.py uses
  * torch.distributed.broadcast over NVLink).  Sender: bm25x_index_get_layout.  Receiver: bm25x_index_alloc_replica

@@ -28,6 +28,16 @@ class _Corpus(C.Structure):
                 ("b", C.c_double)]
 
 
+class _Blocks(C.Structure):
+    _fields_ = [("n_docs", C.c_uint32), ("doc_len", C.POINTER(C.c_uint32)), ("doc_fieldnorm", C.POINTER(C.c_uint8)),
+                ("sum_doc_len", C.c_uint64), ("payload", C.POINTER(C.c_uint16)), ("n_terms", C.c_uint32),
+                ("term_key", C.POINTER(C.c_uint8)), ("term_blk_off", C.POINTER(C.c_uint64)), ("n_blocks", C.c_uint64),
+                ("blk_min_doc", C.POINTER(C.c_uint32)), ("blk_n", C.POINTER(C.c_uint32)),
+                ("blk_meta_doc", C.POINTER(C.c_uint8)), ("blk_meta_tf", C.POINTER(C.c_uint8)),
+                ("blk_doc_off", C.POINTER(C.c_uint64)), ("blk_tf_off", C.POINTER(C.c_uint64)),
+                ("bytes", C.POINTER(C.c_uint8)), ("n_bytes", C.c_uint64), ("k1", C.c_double), ("b", C.c_double)]
+
+
 class IndexInfo(C.Structure):
     _fields_ = [("n_docs", C.c_uint32), ("n_terms", C.c_uint32), ("n_postings", C.c_uint64),
                 ("sum_doc_len", C.c_uint64), ("avgdl", C.c_double), ("k1", C.c_double), ("b", C.c_double),
@@ -80,6 +90,7 @@ def load_library():
                                              C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_float),
                                              C.POINTER(C.c_double))
     L.bm25x_index_create.argtypes = [C.POINTER(_Corpus), C.c_int, C.POINTER(vp)]
+    L.bm25x_index_create_from_blocks.argtypes = [C.POINTER(_Blocks), C.c_int, C.POINTER(vp)]
     L.bm25x_index_destroy.argtypes = [vp]
     L.bm25x_index_destroy.restype = None
     L.bm25x_index_get_info.argtypes = [vp, C.POINTER(IndexInfo)]
@@ -213,6 +224,46 @@ class Index:
         self.h = h
         self._keep = None  # the library copied everything to the device
         self.n_docs, self.n_terms = int(n_docs), int(n_terms)
+
+    @classmethod
+    def from_blocks(cls, n_docs, n_terms, term_blk_off, blk_min_doc, blk_n, blk_meta_doc, blk_meta_tf, blk_doc_off,
+                    blk_tf_off, data, doc_len=None, doc_fieldnorm=None, sum_doc_len=0, k1=1.2, b=0.75, payload=None,
+                    term_keys=None, device=0) -> "Index":
+        """Index from the sealed segment as the reference stores it: per-token chains of 128-posting blocks in the
+        codec of compression.rs, decoded on the GPU (bm25x_index_create_from_blocks).  Document norms come either from
+        exact lengths (`doc_len`) or, as on the pages, from `doc_fieldnorm` + `sum_doc_len`."""
+        L = load_library()
+        c = _Blocks()
+        keep = []
+
+        def arr(a, dt, ct):
+            a = np.ascontiguousarray(a, dtype=dt)
+            keep.append(a)
+            return _p(a, ct)
+
+        c.n_docs, c.n_terms, c.k1, c.b = int(n_docs), int(n_terms), float(k1), float(b)
+        if doc_len is not None:
+            c.doc_len = arr(doc_len, np.uint32, C.c_uint32)
+        if doc_fieldnorm is not None:
+            c.doc_fieldnorm = arr(doc_fieldnorm, np.uint8, C.c_uint8)
+        c.sum_doc_len = int(sum_doc_len)
+        if payload is not None:
+            c.payload = arr(payload, np.uint16, C.c_uint16)
+        if term_keys is not None:
+            c.term_key = arr(term_keys, np.uint8, C.c_uint8)
+        c.term_blk_off = arr(term_blk_off, np.uint64, C.c_uint64)
+        c.n_blocks = int(keep[-1][int(n_terms)]) if len(keep[-1]) > int(n_terms) else 0
+        c.blk_min_doc = arr(blk_min_doc, np.uint32, C.c_uint32)
+        c.blk_n = arr(blk_n, np.uint32, C.c_uint32)
+        c.blk_meta_doc = arr(blk_meta_doc, np.uint8, C.c_uint8)
+        c.blk_meta_tf = arr(blk_meta_tf, np.uint8, C.c_uint8)
+        c.blk_doc_off = arr(blk_doc_off, np.uint64, C.c_uint64)
+        c.blk_tf_off = arr(blk_tf_off, np.uint64, C.c_uint64)
+        c.bytes = arr(data, np.uint8, C.c_uint8)
+        c.n_bytes = len(keep[-1])
+        h = C.c_void_p()
+        _check(L.bm25x_index_create_from_blocks(C.byref(c), device, C.byref(h)))
+        return cls._adopt(h, n_docs, n_terms)
 
     @classmethod
     def _adopt(cls, handle, n_docs, n_terms):

@@ -13,6 +13,7 @@
 #include <algorithm>
 
 #include "bm25x_common.h"
+#include "bm25x_blocks.cuh"
 
 static thread_local char g_err[512] = "";
 
@@ -177,29 +178,201 @@ static int dev_alloc(bm25x_index *ix, T **p, size_t n) {
         }                                                                                           \
     } while (0)
 
+// What both index sources (CSR columns, reference-format blocks) share: statistics, tables, allocations.
+struct BuildMeta {
+    uint32_t n_docs, n_terms;
+    const uint32_t *doc_len;
+    const uint16_t *payload;
+    const uint8_t *term_key;
+    double k1, b;
+    const uint32_t *df;  // [n_terms]
+    uint64_t n_post;
+    const uint8_t *fieldnorm = nullptr;  // when doc_len == NULL: DocumentTuple.fieldnorm per doc + JumpTuple.sum_of_document_lengths
+    uint64_t sum_len = 0;
+};
+
+static int check_common(const char *who, uint32_t n_docs, const void *doc_len, double k1, double b, int device) {
+    if (n_docs == 0 || n_docs == BM25X_DOC_INF || !doc_len) {
+        bm25x_set_error("%s: empty or malformed corpus", who);
+        return BM25X_ERR_INVALID;
+    }
+    if (!(k1 >= 0.0) || !(b >= 0.0 && b <= 1.0)) {
+        bm25x_set_error("%s: k1/b out of range", who);
+        return BM25X_ERR_INVALID;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+        cudaGetLastError();
+        bm25x_set_error("%s: CUDA device %d not available (%d devices); there is no CPU fallback", who, device, ndev);
+        return BM25X_ERR_CUDA;
+    }
+    return BM25X_OK;
+}
+
+static int check_keys(const char *who, const uint8_t *term_key, uint32_t T) {
+    if (term_key)
+        for (uint32_t t = 1; t < T; t++)
+            if (memcmp(term_key + (size_t)(t - 1) * 16, term_key + (size_t)t * 16, 16) >= 0) {
+                bm25x_set_error("%s: term_key must be strictly ascending", who);
+                return BM25X_ERR_INVALID;
+            }
+    return BM25X_OK;
+}
+
+// Allocates the index and fills everything except the postings.  On failure the index is destroyed.
+static int index_begin(const BuildMeta &m, int device, bm25x_index **ixp) {
+    *ixp = nullptr;
+    fn_init();
+    const uint32_t N = m.n_docs, T = m.n_terms;
+    const uint64_t P = m.n_post;
+    bm25x_index *ix = new bm25x_index();
+    ix->device = device;
+    ix->k1 = m.k1;
+    ix->b = m.b;
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        bm25x_set_error("bm25x_index_create: device %d is sm_%d%d; this library only carries sm_100a kernels", device,
+                        prop.major, prop.minor);
+        bm25x_index_destroy(ix);
+        return BM25X_ERR_CUDA;
+    }
+    ix->sm_count = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
+    {   // keep freed batch buffers cached in the default pool (bm25x_batch_* allocate stream-ordered)
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t thr = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+    }
+
+    // ---- flush.rs:52-66: N, Σlen (exact), per-doc fieldnorm (quantised), avgdl ----
+    std::vector<uint8_t> h_fn(N);
+    uint64_t sum_len = 0;
+    if (m.doc_len) {
+#pragma omp parallel for reduction(+ : sum_len)
+        for (uint32_t d = 0; d < N; d++) {
+            sum_len += m.doc_len[d];
+            h_fn[d] = bm25x_length_to_fieldnorm(m.doc_len[d]);
+        }
+    } else {  // the stored index keeps only the quantised norm per document and the exact total (tuples.rs:141-160,756-762)
+        memcpy(h_fn.data(), m.fieldnorm, N);
+        sum_len = m.sum_len;
+    }
+    ix->sum_len = sum_len;
+    ix->avgdl = (double)sum_len / (double)N;
+
+    // ---- per-term df, padded offsets, block offsets, s0 (bm25.rs:285-289,348) ----
+    ix->h_df.resize(T);
+    std::vector<uint64_t> h_off_pad(T + 1), h_blk_off(T + 1);
+    std::vector<double> h_s0d(T);
+    std::vector<float> h_s0f(T);
+    uint64_t pp = 0, nb = 0;
+    for (uint32_t t = 0; t < T; t++) {
+        uint64_t n = m.df[t];
+        ix->h_df[t] = (uint32_t)n;
+        h_off_pad[t] = pp;
+        h_blk_off[t] = nb;
+        pp += (n + 1) & ~(uint64_t)1;
+        nb += (n + BM25X_BLOCK - 1) / BM25X_BLOCK;
+        double idf = log(((double)N + 1.0) / ((double)n + 0.5));
+        h_s0d[t] = idf * (m.k1 + 1.0);
+        h_s0f[t] = (float)h_s0d[t];
+    }
+    h_off_pad[T] = pp;
+    h_blk_off[T] = nb;
+    // bm25.rs:349-352 — identical for every term: depends only on (k1, b, avgdl)
+    double h_s1d[256];
+    float h_s1f[256];
+    for (int f = 0; f < 256; f++) {
+        double dl = (double)g_fn_len[f];
+        h_s1d[f] = m.k1 * (1.0 - m.b + m.b * dl / ix->avgdl);
+        h_s1f[f] = (float)h_s1d[f];
+    }
+    if (m.term_key) ix->h_keys.assign(m.term_key, m.term_key + (size_t)T * 16);
+
+    DeviceIndex &d = ix->d;
+    d.n_docs = N;
+    d.n_terms = T;
+    d.n_post = P;
+    d.n_post_pad = pp;
+    d.n_blocks = nb;
+    TRY(dev_alloc(ix, &d.post, pp + 2));
+    TRY(dev_alloc(ix, &d.post_off, (size_t)T + 1));
+    TRY(dev_alloc(ix, &d.df, T));
+    TRY(dev_alloc(ix, &d.blk_off, (size_t)T + 1));
+    TRY(dev_alloc(ix, &d.blk, nb));
+    TRY(dev_alloc(ix, &d.s0f, T));
+    TRY(dev_alloc(ix, &d.s0d, T));
+    TRY(dev_alloc(ix, &d.s1d, 256));
+    TRY(dev_alloc(ix, &d.s1f, 256));
+    TRY(dev_alloc(ix, &d.ubd, T));
+    TRY(dev_alloc(ix, &d.fieldnorm, N));
+    TRY(dev_alloc(ix, &d.payload, (size_t)N * 3));
+    CU(cudaMemset((void *)(d.post + pp), 0xFF, 2 * sizeof(Posting)));  // the two slack slots read as exhausted cursors
+    CU(cudaMemcpy(d.post_off, h_off_pad.data(), sizeof(uint64_t) * (T + 1), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d.blk_off, h_blk_off.data(), sizeof(uint64_t) * (T + 1), cudaMemcpyHostToDevice));
+    if (T) {
+        CU(cudaMemcpy(d.df, ix->h_df.data(), sizeof(uint32_t) * T, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(d.s0d, h_s0d.data(), sizeof(double) * T, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(d.s0f, h_s0f.data(), sizeof(float) * T, cudaMemcpyHostToDevice));
+    }
+    CU(cudaMemcpy(d.s1d, h_s1d, sizeof(h_s1d), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d.s1f, h_s1f, sizeof(h_s1f), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d.fieldnorm, h_fn.data(), N, cudaMemcpyHostToDevice));
+    if (m.payload) {
+        CU(cudaMemcpy(d.payload, m.payload, sizeof(uint16_t) * 3 * (size_t)N, cudaMemcpyHostToDevice));
+    } else {
+        std::vector<uint16_t> pl((size_t)N * 3);
+        for (uint32_t i = 0; i < N; i++) {  // synthetic ctid: (block hi, block lo, offset) of a 291-tuple page
+            uint32_t blkno = i / 291;
+            pl[(size_t)i * 3 + 0] = (uint16_t)(blkno >> 16);
+            pl[(size_t)i * 3 + 1] = (uint16_t)(blkno & 0xFFFF);
+            pl[(size_t)i * 3 + 2] = (uint16_t)(i % 291 + 1);
+        }
+        CU(cudaMemcpy(d.payload, pl.data(), sizeof(uint16_t) * pl.size(), cudaMemcpyHostToDevice));
+    }
+
+    *ixp = ix;
+    return BM25X_OK;
+}
+
+// After the postings are in place: pad slots, block descriptors, per-term score bounds.
+static cudaError_t index_finish_device(bm25x_index *ix) {
+    DeviceIndex &d = ix->d;
+    const uint32_t T = d.n_terms;
+    const uint64_t nb = d.n_blocks;
+    cudaError_t e = cudaSuccess;
+    if (T) {
+        k_pad_slots<<<(T + 255) / 256, 256>>>(d.post_off, d.df, T, d.post);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess && nb) {
+        k_block_desc<<<(unsigned)((nb + 255) / 256), 256>>>(d.post_off, d.df, d.blk_off, T, nb, d.post, d.blk);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess && T) {
+        k_term_ub<<<(unsigned)std::min<uint32_t>(T, 148u * 16u), 256>>>(d.post_off, d.df, d.post, d.s0d, d.s1d, T, d.ubd);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    return e;
+}
+
 extern "C" int bm25x_index_create(const bm25x_corpus *c, int device, bm25x_index **out) {
     if (!c || !out) {
         bm25x_set_error("bm25x_index_create: null argument");
         return BM25X_ERR_INVALID;
     }
     *out = nullptr;
-    if (c->n_docs == 0 || c->n_docs == BM25X_DOC_INF || !c->doc_len || !c->post_off ||
-        (c->post_off[c->n_terms] && (!c->post_doc || !c->post_tf))) {
+    if (!c->post_off || (c->post_off[c->n_terms] && (!c->post_doc || !c->post_tf))) {
         bm25x_set_error("bm25x_index_create: empty or malformed corpus");
         return BM25X_ERR_INVALID;
     }
-    if (!(c->k1 >= 0.0) || !(c->b >= 0.0 && c->b <= 1.0)) {
-        bm25x_set_error("bm25x_index_create: k1/b out of range");
-        return BM25X_ERR_INVALID;
-    }
-    int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
-        cudaGetLastError();
-        bm25x_set_error("bm25x_index_create: CUDA device %d not available (%d devices); there is no CPU fallback",
-                        device, ndev);
-        return BM25X_ERR_CUDA;
-    }
-    fn_init();
+    int rc = check_common("bm25x_index_create", c->n_docs, c->doc_len, c->k1, c->b, device);
+    if (rc != BM25X_OK) return rc;
     const uint32_t N = c->n_docs, T = c->n_terms;
     const uint64_t P = c->post_off[T];
 
@@ -229,117 +402,16 @@ extern "C" int bm25x_index_create(const bm25x_corpus *c, int device, bm25x_index
         bm25x_set_error("bm25x_index_create: term frequency >= 2^24 is not supported by the packed posting layout");
         return BM25X_ERR_UNSUPPORTED;
     }
-    if (c->term_key) {
-        for (uint32_t t = 1; t < T; t++)
-            if (memcmp(c->term_key + (size_t)(t - 1) * 16, c->term_key + (size_t)t * 16, 16) >= 0) {
-                bm25x_set_error("bm25x_index_create: term_key must be strictly ascending");
-                return BM25X_ERR_INVALID;
-            }
-    }
+    rc = check_keys("bm25x_index_create", c->term_key, T);
+    if (rc != BM25X_OK) return rc;
 
-    bm25x_index *ix = new bm25x_index();
-    ix->device = device;
-    ix->k1 = c->k1;
-    ix->b = c->b;
-    CU(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    CU(cudaGetDeviceProperties(&prop, device));
-    if (prop.major != 10) {
-        bm25x_set_error("bm25x_index_create: device %d is sm_%d%d; this library only carries sm_100a kernels", device,
-                        prop.major, prop.minor);
-        bm25x_index_destroy(ix);
-        return BM25X_ERR_CUDA;
-    }
-    ix->sm_count = prop.multiProcessorCount;
-    CU(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
-    {   // keep freed batch buffers cached in the default pool (bm25x_batch_* allocate stream-ordered)
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-            uint64_t thr = ~0ull;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-        }
-    }
-
-    // ---- flush.rs:52-66: N, Σlen (exact), per-doc fieldnorm (quantised), avgdl ----
-    std::vector<uint8_t> h_fn(N);
-    uint64_t sum_len = 0;
-#pragma omp parallel for reduction(+ : sum_len)
-    for (uint32_t d = 0; d < N; d++) {
-        sum_len += c->doc_len[d];
-        h_fn[d] = bm25x_length_to_fieldnorm(c->doc_len[d]);
-    }
-    ix->sum_len = sum_len;
-    ix->avgdl = (double)sum_len / (double)N;
-
-    // ---- per-term df, padded offsets, block offsets, s0 (bm25.rs:285-289,348) ----
-    ix->h_df.resize(T);
-    std::vector<uint64_t> h_off_pad(T + 1), h_blk_off(T + 1);
-    std::vector<double> h_s0d(T);
-    std::vector<float> h_s0f(T);
-    uint64_t pp = 0, nb = 0;
-    for (uint32_t t = 0; t < T; t++) {
-        uint64_t n = c->post_off[t + 1] - c->post_off[t];
-        ix->h_df[t] = (uint32_t)n;
-        h_off_pad[t] = pp;
-        h_blk_off[t] = nb;
-        pp += (n + 1) & ~(uint64_t)1;
-        nb += (n + BM25X_BLOCK - 1) / BM25X_BLOCK;
-        double idf = log(((double)N + 1.0) / ((double)n + 0.5));
-        h_s0d[t] = idf * (c->k1 + 1.0);
-        h_s0f[t] = (float)h_s0d[t];
-    }
-    h_off_pad[T] = pp;
-    h_blk_off[T] = nb;
-    // bm25.rs:349-352 — identical for every term: depends only on (k1, b, avgdl)
-    double h_s1d[256];
-    float h_s1f[256];
-    for (int f = 0; f < 256; f++) {
-        double dl = (double)g_fn_len[f];
-        h_s1d[f] = c->k1 * (1.0 - c->b + c->b * dl / ix->avgdl);
-        h_s1f[f] = (float)h_s1d[f];
-    }
-    if (c->term_key) ix->h_keys.assign(c->term_key, c->term_key + (size_t)T * 16);
-
+    std::vector<uint32_t> df(T);
+    for (uint32_t t = 0; t < T; t++) df[t] = (uint32_t)(c->post_off[t + 1] - c->post_off[t]);
+    BuildMeta m{N, T, c->doc_len, c->payload, c->term_key, c->k1, c->b, df.data(), P};
+    bm25x_index *ix = nullptr;
+    rc = index_begin(m, device, &ix);
+    if (rc != BM25X_OK) return rc;
     DeviceIndex &d = ix->d;
-    d.n_docs = N;
-    d.n_terms = T;
-    d.n_post = P;
-    d.n_post_pad = pp;
-    d.n_blocks = nb;
-    TRY(dev_alloc(ix, &d.post, pp + 2));
-    TRY(dev_alloc(ix, &d.post_off, (size_t)T + 1));
-    TRY(dev_alloc(ix, &d.df, T));
-    TRY(dev_alloc(ix, &d.blk_off, (size_t)T + 1));
-    TRY(dev_alloc(ix, &d.blk, nb));
-    TRY(dev_alloc(ix, &d.s0f, T));
-    TRY(dev_alloc(ix, &d.s0d, T));
-    TRY(dev_alloc(ix, &d.s1d, 256));
-    TRY(dev_alloc(ix, &d.s1f, 256));
-    TRY(dev_alloc(ix, &d.ubd, T));
-    TRY(dev_alloc(ix, &d.fieldnorm, N));
-    TRY(dev_alloc(ix, &d.payload, (size_t)N * 3));
-    CU(cudaMemcpy(d.post_off, h_off_pad.data(), sizeof(uint64_t) * (T + 1), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(d.blk_off, h_blk_off.data(), sizeof(uint64_t) * (T + 1), cudaMemcpyHostToDevice));
-    if (T) {
-        CU(cudaMemcpy(d.df, ix->h_df.data(), sizeof(uint32_t) * T, cudaMemcpyHostToDevice));
-        CU(cudaMemcpy(d.s0d, h_s0d.data(), sizeof(double) * T, cudaMemcpyHostToDevice));
-        CU(cudaMemcpy(d.s0f, h_s0f.data(), sizeof(float) * T, cudaMemcpyHostToDevice));
-    }
-    CU(cudaMemcpy(d.s1d, h_s1d, sizeof(h_s1d), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(d.s1f, h_s1f, sizeof(h_s1f), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(d.fieldnorm, h_fn.data(), N, cudaMemcpyHostToDevice));
-    if (c->payload) {
-        CU(cudaMemcpy(d.payload, c->payload, sizeof(uint16_t) * 3 * (size_t)N, cudaMemcpyHostToDevice));
-    } else {
-        std::vector<uint16_t> pl((size_t)N * 3);
-        for (uint32_t i = 0; i < N; i++) {  // synthetic ctid: (block hi, block lo, offset) of a 291-tuple page
-            uint32_t blkno = i / 291;
-            pl[(size_t)i * 3 + 0] = (uint16_t)(blkno >> 16);
-            pl[(size_t)i * 3 + 1] = (uint16_t)(blkno & 0xFFFF);
-            pl[(size_t)i * 3 + 2] = (uint16_t)(i % 291 + 1);
-        }
-        CU(cudaMemcpy(d.payload, pl.data(), sizeof(uint16_t) * pl.size(), cudaMemcpyHostToDevice));
-    }
 
     // ---- postings: chunked H2D of the CSR columns + device transform to the padded AoS ----
     {
@@ -363,19 +435,7 @@ extern "C" int bm25x_index_create(const bm25x_corpus *c, int device, bm25x_index
             }
             if (e == cudaSuccess) e = cudaDeviceSynchronize();
         }
-        if (e == cudaSuccess && T) {
-            k_pad_slots<<<(T + 255) / 256, 256>>>(d.post_off, d.df, T, d.post);
-            e = cudaGetLastError();
-        }
-        if (e == cudaSuccess && nb) {
-            k_block_desc<<<(unsigned)((nb + 255) / 256), 256>>>(d.post_off, d.df, d.blk_off, T, nb, d.post, d.blk);
-            e = cudaGetLastError();
-        }
-        if (e == cudaSuccess && T) {
-            k_term_ub<<<(unsigned)std::min<uint32_t>(T, 148u * 16u), 256>>>(d.post_off, d.df, d.post, d.s0d, d.s1d, T, d.ubd);
-            e = cudaGetLastError();
-        }
-        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        if (e == cudaSuccess) e = index_finish_device(ix);
         cudaFree(d_off);
         cudaFree(d_cdoc);
         cudaFree(d_ctf);
@@ -384,6 +444,143 @@ extern "C" int bm25x_index_create(const bm25x_corpus *c, int device, bm25x_index
             bm25x_index_destroy(ix);
             return e == cudaErrorMemoryAllocation ? BM25X_ERR_OOM : BM25X_ERR_CUDA;
         }
+    }
+    *out = ix;
+    return BM25X_OK;
+}
+
+// ---- f1: the sealed segment as the reference stores it (blocks in the codec of compression.rs), decoded on the GPU ----
+extern "C" int bm25x_index_create_from_blocks(const bm25x_blocks *c, int device, bm25x_index **out) {
+    const char *who = "bm25x_index_create_from_blocks";
+    if (!c || !out) {
+        bm25x_set_error("%s: null argument", who);
+        return BM25X_ERR_INVALID;
+    }
+    *out = nullptr;
+    const uint32_t N = c->n_docs, T = c->n_terms;
+    const uint64_t NB = c->n_blocks;
+    if (!c->term_blk_off || (NB && (!c->blk_min_doc || !c->blk_n || !c->blk_meta_doc || !c->blk_meta_tf ||
+                                    !c->blk_doc_off || !c->blk_tf_off || (c->n_bytes && !c->bytes)))) {
+        bm25x_set_error("%s: empty or malformed corpus", who);
+        return BM25X_ERR_INVALID;
+    }
+    int rc = check_common(who, N, c->doc_len ? (const void *)c->doc_len : (const void *)c->doc_fieldnorm, c->k1, c->b, device);
+    if (rc != BM25X_OK) return rc;
+    if (c->term_blk_off[0] != 0 || c->term_blk_off[T] != NB) {
+        bm25x_set_error("%s: term_blk_off must run from 0 to n_blocks", who);
+        return BM25X_ERR_INVALID;
+    }
+    // ---- host-side validation of the block directory (payloads are validated by the decoder on the device) ----
+    std::vector<uint32_t> df(T);
+    uint64_t P = 0;
+    int bad = 0;
+#pragma omp parallel for schedule(dynamic, 256) reduction(| : bad) reduction(+ : P)
+    for (uint32_t t = 0; t < T; t++) {
+        const uint64_t b0 = c->term_blk_off[t], b1 = c->term_blk_off[t + 1];
+        if (b1 < b0 || b1 > NB) {
+            bad |= 1;
+            df[t] = 0;
+            continue;
+        }
+        uint64_t n_t = 0;
+        for (uint64_t g = b0; g < b1; g++) {
+            const uint32_t n = c->blk_n[g];
+            // flush.rs:80-90: every block of a token holds 128 postings except the last one
+            if (n == 0 || n > BM25X_BLOCK || (n < BM25X_BLOCK && g + 1 != b1)) bad |= 1;
+            const uint8_t metas[2] = {c->blk_meta_doc[g], c->blk_meta_tf[g]};
+            const uint64_t offs[2] = {c->blk_doc_off[g], c->blk_tf_off[g]};
+            for (int s = 0; s < 2; s++) {
+                const uint32_t w = metas[s] & 0x7Fu;
+                uint64_t nbytes;
+                if ((metas[s] >> 7) == 0) {  // compression.rs:43-52: bit packing only for full blocks, width <= 32
+                    if (w > 32 || n != BM25X_BLOCK) bad |= 2;
+                    nbytes = (uint64_t)w * 16;
+                } else {                      // compression.rs:53-62: 1..4 bytes per value
+                    if (w < 1 || w > 4) bad |= 2;
+                    nbytes = (uint64_t)w * n;
+                }
+                if (offs[s] > c->n_bytes || nbytes > c->n_bytes - offs[s]) bad |= 1;
+            }
+            n_t += n;
+        }
+        if (n_t > N) bad |= 1;
+        df[t] = (uint32_t)std::min<uint64_t>(n_t, N);
+        P += n_t;
+    }
+    if (bad & 1) {
+        bm25x_set_error("%s: corrupt block directory (block sizes, token ranges or payload offsets)", who);
+        return BM25X_ERR_INVALID;
+    }
+    if (bad & 2) {
+        bm25x_set_error("%s: corrupt block metadata (bitwidth out of bound / unexpected input len)", who);
+        return BM25X_ERR_INVALID;
+    }
+    rc = check_keys(who, c->term_key, T);
+    if (rc != BM25X_OK) return rc;
+
+    BuildMeta m{N, T, c->doc_len, c->payload, c->term_key, c->k1, c->b, df.data(), P};
+    m.fieldnorm = c->doc_fieldnorm;
+    m.sum_len = c->sum_doc_len;
+    bm25x_index *ix = nullptr;
+    rc = index_begin(m, device, &ix);
+    if (rc != BM25X_OK) return rc;
+    DeviceIndex &d = ix->d;
+
+    // ---- upload the directory + payloads, decode on the device ----
+    uint64_t *d_tbo = nullptr, *d_doff = nullptr, *d_toff = nullptr;
+    uint32_t *d_min = nullptr, *d_n = nullptr, *d_err = nullptr;
+    uint8_t *d_md = nullptr, *d_mt = nullptr, *d_bytes = nullptr;
+    uint32_t h_err = 0;
+    cudaError_t e = cudaSuccess;
+    auto up = [&](auto **dp, const auto *hp, size_t n) {
+        using E = std::remove_pointer_t<std::remove_pointer_t<decltype(dp)>>;
+        if (e != cudaSuccess) return;
+        e = cudaMalloc((void **)dp, sizeof(E) * (n ? n : 1));
+        if (e == cudaSuccess && n) e = cudaMemcpy(*dp, hp, sizeof(E) * n, cudaMemcpyHostToDevice);
+    };
+    up(&d_tbo, c->term_blk_off, (size_t)T + 1);
+    up(&d_min, c->blk_min_doc, NB);
+    up(&d_n, c->blk_n, NB);
+    up(&d_md, c->blk_meta_doc, NB);
+    up(&d_mt, c->blk_meta_tf, NB);
+    up(&d_doff, c->blk_doc_off, NB);
+    up(&d_toff, c->blk_tf_off, NB);
+    up(&d_bytes, c->bytes, c->n_bytes);
+    up(&d_err, &h_err, 1);
+    if (e == cudaSuccess && NB) {
+        k_decode_blocks<<<(unsigned)((NB + DEC_WARPS - 1) / DEC_WARPS), DEC_WARPS * 32>>>(
+            NB, d_tbo, T, d_min, d_n, d_md, d_mt, d_doff, d_toff, d_bytes, d.post_off, d.fieldnorm, N, d.post, d_err);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = index_finish_device(ix);
+    if (e == cudaSuccess && NB > 1) {
+        k_check_block_order<<<(unsigned)((NB + 255) / 256), 256>>>(d.blk_off, T, NB, d.blk, d_err);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(&h_err, d_err, sizeof(h_err), cudaMemcpyDeviceToHost);
+    cudaFree(d_tbo);
+    cudaFree(d_min);
+    cudaFree(d_n);
+    cudaFree(d_md);
+    cudaFree(d_mt);
+    cudaFree(d_doff);
+    cudaFree(d_toff);
+    cudaFree(d_bytes);
+    cudaFree(d_err);
+    if (e != cudaSuccess) {
+        bm25x_set_error("%s: block upload/decode failed: %s", who, cudaGetErrorString(e));
+        bm25x_index_destroy(ix);
+        return e == cudaErrorMemoryAllocation ? BM25X_ERR_OOM : BM25X_ERR_CUDA;
+    }
+    if (h_err & BM25X_BLKERR_RANGE) {
+        bm25x_set_error("%s: corrupt blocks (doc ids must be < n_docs and strictly ascending per token, tf != 0)", who);
+        bm25x_index_destroy(ix);
+        return BM25X_ERR_INVALID;
+    }
+    if (h_err & BM25X_BLKERR_TF) {
+        bm25x_set_error("%s: term frequency >= 2^24 is not supported by the packed posting layout", who);
+        bm25x_index_destroy(ix);
+        return BM25X_ERR_UNSUPPORTED;
     }
     *out = ix;
     return BM25X_OK;
