@@ -8,7 +8,8 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "libbm25x.so")
+# BM25X_LIBRARY: load another build of the same library (tools/time_variants.py times tuning variants side by side)
+_SO = os.environ.get("BM25X_LIBRARY") or os.path.join(_HERE, "libbm25x.so")
 
 MAX_K = 1024
 MAX_QUERY_TERMS = 32

@@ -15,16 +15,33 @@
 
 namespace {
 
+// Tuning knobs (compile time; the defaults are the measured best on C3, profiles/README.md)
+#ifndef BM25X_AU
+#define BM25X_AU 4
+#endif
+#ifndef BM25X_BU
+#define BM25X_BU 4
+#endif
+#ifndef BM25X_NSUB_SMALL
+#define BM25X_NSUB_SMALL 1
+#endif
+#ifndef BM25X_LOG_S
+#define BM25X_LOG_S 12
+#endif
+
 template <int M_, int KP_>
 struct WCfg {
     static constexpr int M = M_;                    // max live terms (lanes 0..M-1 own the terms)
     static constexpr int KP = KP_;                  // pool capacity (power of two >= k + LCAP)
     // block budget per chunk (Σ quota = CB exactly): two 128-posting blocks per term for m = M <= 4
     static constexpr int CB = 2 * M_;
-    static constexpr int SUB_TARGET = 640;          // postings per tag-map sub-window (classes with more than 4 terms)
+    static constexpr int LOG_S = BM25X_LOG_S;       // tag map slots (bytes)
+    static constexpr int SUB_TARGET = 640 >> (12 - LOG_S);  // postings per tag-map sub-window (classes with more than 4 terms)
     static constexpr int NSTG = 1;                  // stages per warp: 1 = rely on the other warps to hide the load latency
-    static constexpr int LOG_S = 12;                // tag map slots (bytes)
     static constexpr int LCAP = 64;                 // candidate / possible-duplicate list entries
+    static constexpr int AU = BM25X_AU;             // mark phase: postings per lane and trip (independent loads in flight)
+    static constexpr int BU = BM25X_BU;             // test phase: postings per lane and trip
+    static constexpr int NSUB_SMALL = BM25X_NSUB_SMALL;  // sub-windows per chunk for classes up to 4 terms
     static constexpr int STAGE_POSTINGS = (CB + M_) * (int)BM25X_BLOCK;  // + one partially consumed block per run
     static constexpr size_t stage_bytes = (size_t)STAGE_POSTINGS * sizeof(Posting);
     // per-warp shared memory
@@ -396,7 +413,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_wq(const __grid_consta
             // The chunk is processed in doc sub-windows of at most ~SUB_TARGET postings: loads can be large while the
             // tag map only ever has to unite a few hundred postings.
             // (classes up to 4 terms load two blocks per term: one sub-window, resolved at compile time)
-            uint32_t nsub = 1u;
+            uint32_t nsub = (uint32_t)C::NSUB_SMALL;
             if (C::M > 4) {
                 const uint32_t chunk_postings = __reduce_add_sync(0xFFFFFFFFu, run_e - run_a);
                 nsub = max(1u, (chunk_postings + C::SUB_TARGET - 1) / C::SUB_TARGET);
@@ -491,44 +508,69 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_wq(const __grid_consta
                 for (uint32_t j = 0; j < m; ++j) {
                     const uint32_t a = __shfl_sync(0xFFFFFFFFu, my_a, j), e = __shfl_sync(0xFFFFFFFFu, my_e, j);
                     const uint8_t tagv = (uint8_t)(j + 1);
-                    for (uint32_t i = a + lane; i < e; i += 32) map[slot_of<C::LOG_S>(st[i].doc)] = tagv;
+                    // AU postings per lane and trip while whole trips remain (independent loads in flight), then singly
+                    uint32_t i = a + lane;
+                    if (C::AU > 1) {
+                        for (; i + 32u * (C::AU - 1) < e; i += 32 * C::AU) {
+                            uint32_t dd[C::AU];
+#pragma unroll
+                            for (int u = 0; u < C::AU; ++u) dd[u] = st[i + 32u * u].doc;
+#pragma unroll
+                            for (int u = 0; u < C::AU; ++u) map[slot_of<C::LOG_S>(dd[u])] = tagv;
+                        }
+                    }
+                    for (; i < e; i += 32) map[slot_of<C::LOG_S>(st[i].doc)] = tagv;
                 }
                 __syncwarp();
             }
-            // ---- B: test; score + filter the singles; list the possible duplicates (2 postings per lane) ----
+            // ---- B: test; score + filter the singles; list the possible duplicates (BU postings per lane) ----
             for (uint32_t j = 0; j < m && !dense; ++j) {
                 const uint32_t a = __shfl_sync(0xFFFFFFFFu, my_a, j), e = __shfl_sync(0xFFFFFFFFu, my_e, j);
                 const float ctf = __shfl_sync(0xFFFFFFFFu, f.ctf, j);
-                const uint8_t tagv = (uint8_t)(j + 1);
-                for (uint32_t base = a; base < e; base += 64) {
-                    const uint32_t i0 = base + lane, i1 = i0 + 32;
-                    const bool v0 = i0 < e, v1 = i1 < e;
-                    const Posting p0 = st[v0 ? i0 : a], p1 = st[v1 ? i1 : a];
-                    uint8_t t0 = tagv, t1 = tagv;
-                    if (multi) {
-                        t0 = map[slot_of<C::LOG_S>(p0.doc)];
-                        t1 = map[slot_of<C::LOG_S>(p1.doc)];
+                const uint32_t tagv = j + 1u;
+                for (uint32_t base = a; base < e; base += 32 * C::BU) {
+                    uint32_t idx[C::BU];
+                    Posting pp[C::BU];
+                    bool vv[C::BU], dd[C::BU], gg[C::BU];
+#pragma unroll
+                    for (int u = 0; u < C::BU; ++u) {
+                        idx[u] = base + lane + 32u * u;
+                        vv[u] = idx[u] < e;
+                        pp[u] = st[vv[u] ? idx[u] : a];
                     }
-                    const bool d0 = v0 && t0 != tagv, d1 = v1 && t1 != tagv;
-                    // threshold test in the tf domain (no division); signature tie rule as in wfilter_pass
-                    const bool g0 = (float)(p0.w >> 8) >= ctf * s1f[p0.w & 0xFFu];
-                    const bool g1 = (float)(p1.w >> 8) >= ctf * s1f[p1.w & 0xFFu];
-                    const bool c0 = v0 && !d0 && g0 && !(make_sig(j, p0.w) == f.tie_sig && p0.doc > f.tie_dk);
-                    const bool c1 = v1 && !d1 && g1 && !(make_sig(j, p1.w) == f.tie_sig && p1.doc > f.tie_dk);
-                    const uint32_t md0 = __ballot_sync(0xFFFFFFFFu, d0), md1 = __ballot_sync(0xFFFFFFFFu, d1);
-                    if (md0 | md1) {
-                        const uint32_t q0 = nd + __popc(md0 & lt_mask), q1 = nd + __popc(md0) + __popc(md1 & lt_mask);
-                        if (d0 && q0 < (uint32_t)C::LCAP) dupl[q0] = (j << 16) | i0;
-                        if (d1 && q1 < (uint32_t)C::LCAP) dupl[q1] = (j << 16) | i1;
-                        nd += __popc(md0) + __popc(md1);
+                    bool anyd = false, anyg = false;
+#pragma unroll
+                    for (int u = 0; u < C::BU; ++u) {
+                        const uint32_t t = multi ? (uint32_t)map[slot_of<C::LOG_S>(pp[u].doc)] : tagv;
+                        dd[u] = vv[u] && t != tagv;
+                        // threshold test in the tf domain (no division), unconditional: no branches; the signature
+                        // tie rule is only evaluated for the few postings that get this far
+                        const float r = ctf * s1f[pp[u].w & 0xFFu];
+                        gg[u] = ((float)(pp[u].w >> 8) >= r) & vv[u] & !dd[u];
+                        anyd |= dd[u];
+                        anyg |= gg[u];
+                    }
+                    if (__any_sync(0xFFFFFFFFu, anyd)) {
+                        uint32_t q = nd;
+#pragma unroll
+                        for (int u = 0; u < C::BU; ++u) {
+                            const uint32_t md = __ballot_sync(0xFFFFFFFFu, dd[u]);
+                            const uint32_t qq = q + __popc(md & lt_mask);
+                            if (dd[u] && qq < (uint32_t)C::LCAP) dupl[qq] = (j << 16) | idx[u];
+                            q += __popc(md);
+                        }
+                        nd = q;
                         if (nd > (uint32_t)C::LCAP) {
                             dense = true;
                             break;
                         }
                     }
-                    if (__any_sync(0xFFFFFFFFu, c0 | c1)) {
-                        push_cand(c0, (j << 16) | i0);
-                        push_cand(c1, (j << 16) | i1);
+                    if (__any_sync(0xFFFFFFFFu, anyg)) {
+#pragma unroll
+                        for (int u = 0; u < C::BU; ++u) {
+                            const bool c = gg[u] && !(make_sig(j, pp[u].w) == f.tie_sig && pp[u].doc > f.tie_dk);
+                            push_cand(c, (j << 16) | idx[u]);
+                        }
                     }
                 }
             }
