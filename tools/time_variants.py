@@ -48,7 +48,7 @@ def main():
         env = dict(os.environ, BM25X_LIBRARY=lib)
         try:
             p = subprocess.run([sys.executable, __file__, "--one", str(docs)], env=env, capture_output=True, text=True,
-                               timeout=240)
+                               timeout=75)
             line = [l for l in p.stdout.splitlines() if l.startswith("VARIANT ")]
             res[name] = json.loads(line[-1][8:]) if line else {"error": (p.stderr or p.stdout)[-400:]}
         except subprocess.TimeoutExpired:

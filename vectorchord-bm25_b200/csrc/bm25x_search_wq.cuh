@@ -15,7 +15,8 @@
 
 namespace {
 
-// Tuning knobs (compile time; the defaults are the measured best on C3, profiles/README.md)
+// Tuning knobs (compile time).  The defaults are the measured best of tools/time_variants.py on the 10M-doc corpus
+// (profiles/README.md, "variants"): -1 = choose per class.
 #ifndef BM25X_AU
 #define BM25X_AU 4
 #endif
@@ -26,7 +27,19 @@ namespace {
 #define BM25X_NSUB_SMALL 1
 #endif
 #ifndef BM25X_LOG_S
-#define BM25X_LOG_S 12
+#define BM25X_LOG_S -1
+#endif
+#ifndef BM25X_CBMUL
+#define BM25X_CBMUL 2
+#endif
+#ifndef BM25X_SUBT
+#define BM25X_SUBT 640
+#endif
+#ifndef BM25X_TWOMAP
+#define BM25X_TWOMAP -1
+#endif
+#ifndef BM25X_EXACTQ
+#define BM25X_EXACTQ 1
 #endif
 
 template <int M_, int KP_>
@@ -34,15 +47,25 @@ struct WCfg {
     static constexpr int M = M_;                    // max live terms (lanes 0..M-1 own the terms)
     static constexpr int KP = KP_;                  // pool capacity (power of two >= k + LCAP)
     // block budget per chunk (Σ quota = CB exactly): two 128-posting blocks per term for m = M <= 4
-    static constexpr int CB = 2 * M_;
-    static constexpr int LOG_S = BM25X_LOG_S;       // tag map slots (bytes)
-    static constexpr int SUB_TARGET = 640 >> (12 - LOG_S);  // postings per tag-map sub-window (classes with more than 4 terms)
+    static constexpr int CB = BM25X_CBMUL * M_;
+    // tag map bytes: queries of 5+ terms unite many more postings per window and see far more slot collisions
+    static constexpr int LOG_S = BM25X_LOG_S > 0 ? BM25X_LOG_S : (M_ > 4 ? 13 : 12);
+    static constexpr int SUB_TARGET = LOG_S >= 12 ? (BM25X_SUBT << (LOG_S - 12)) : (BM25X_SUBT >> (12 - LOG_S));  // postings per tag-map sub-window (classes with more than 4 terms)
     static constexpr int NSTG = 1;                  // stages per warp: 1 = rely on the other warps to hide the load latency
     static constexpr int LCAP = 64;                 // candidate / possible-duplicate list entries
     static constexpr int AU = BM25X_AU;             // mark phase: postings per lane and trip (independent loads in flight)
     static constexpr int BU = BM25X_BU;             // test phase: postings per lane and trip
     static constexpr int NSUB_SMALL = BM25X_NSUB_SMALL;  // sub-windows per chunk for classes up to 4 terms
-    static constexpr int STAGE_POSTINGS = (CB + M_) * (int)BM25X_BLOCK;  // + one partially consumed block per run
+    // Two half-size tag maps under independent hashes instead of one: a posting is a possible duplicate only when its
+    // tag lost BOTH slots (a later run holding the same document overwrites both), which squares the false-alarm rate
+    // (pays for its extra hash + byte load per posting only where collisions are frequent: the 5+ term classes)
+    static constexpr bool TWOMAP = BM25X_TWOMAP >= 0 ? BM25X_TWOMAP != 0 : (M_ > 4);
+    static constexpr int LOG_M = TWOMAP ? LOG_S - 1 : LOG_S;
+    // Loads of exactly quota*128 postings from where the last window ended (window end = doc id of the first posting
+    // not loaded, one 4-byte read) instead of loads ending on block boundaries: no half-used blocks in the stage
+    static constexpr bool EXACTQ = BM25X_EXACTQ != 0;
+    static constexpr int STAGE_POSTINGS = EXACTQ ? CB * (int)BM25X_BLOCK  // every run: at most quota*128 postings
+                                                 : (CB + M_) * (int)BM25X_BLOCK;  // + one partially consumed block per run
     static constexpr size_t stage_bytes = (size_t)STAGE_POSTINGS * sizeof(Posting);
     // per-warp shared memory
     static constexpr size_t off_stage = 0;
@@ -85,6 +108,34 @@ struct WarpState {
     uint32_t gpos, next_doc, lo, chunk;
 };
 
+// Tag-map slots of a document (see WCfg::TWOMAP) and the three questions asked of the map.
+template <class C>
+__device__ __forceinline__ uint32_t slot1(uint32_t doc) { return (doc * 0x9E3779B1u) >> (32 - C::LOG_M); }
+template <class C>
+__device__ __forceinline__ uint32_t slot2(uint32_t doc) { return (1u << C::LOG_M) + ((doc * 0x85EBCA77u) >> (32 - C::LOG_M)); }
+template <class C>
+__device__ __forceinline__ void tag_mark(uint8_t *map, uint32_t doc, uint8_t tag) {
+    map[slot1<C>(doc)] = tag;
+    if (C::TWOMAP) map[slot2<C>(doc)] = tag;
+}
+// true: no later run holds this document (the tag survived in a slot that every holder of the document writes)
+template <class C>
+__device__ __forceinline__ bool tag_intact(const uint8_t *map, uint32_t doc, uint32_t tag) {
+    const uint32_t t1 = map[slot1<C>(doc)];
+    if (!C::TWOMAP) return t1 == tag;
+    const uint32_t t2 = map[slot2<C>(doc)];
+    return (t1 == tag) | (t2 == tag);
+}
+// The last run holding the document either kept a slot — then it is the smaller of the two slot owners, later runs can
+// only have taken the other one — or lost both and is listed as a possible duplicate itself.
+template <class C>
+__device__ __forceinline__ uint32_t tag_winner(const uint8_t *map, uint32_t doc) {
+    const uint32_t t1 = map[slot1<C>(doc)];
+    if (!C::TWOMAP) return t1 - 1u;
+    const uint32_t t2 = map[slot2<C>(doc)];
+    return min(t1, t2) - 1u;
+}
+
 // Plans the next chunk.  Loads start at the exact posting where the previous window ended (rounded down to the
 // 16-byte TMA granule) and end on the block boundary chosen by the quota rule, so nothing is scanned twice.
 // First half of the planner: issue the one global load the plan needs (first doc of the block just past my quota).
@@ -93,9 +144,14 @@ template <class C>
 __device__ __forceinline__ uint32_t plan_prefetch(const SearchParams &p, const WarpState<C> &w, int lane) {
     const bool act = lane < (int)w.m && w.gpos < w.dfj && !((w.ne_mask >> lane) & 1u);
     const uint32_t quota = act ? (w.chunk < 2 ? 1u : w.quota_full) : 0u;
-    const uint32_t ib = w.gpos / BM25X_BLOCK;
     uint32_t prop = INF;
-    if (act && ib + quota < w.nb) prop = __ldg(&p.blk[w.bbase + ib + quota].x);
+    if (C::EXACTQ) {
+        const uint32_t endp = (w.gpos & ~1u) + quota * BM25X_BLOCK;  // first posting past my load
+        if (act && endp < w.dfj) prop = __ldg(&p.post[w.pbase + endp].doc);
+    } else {
+        const uint32_t ib = w.gpos / BM25X_BLOCK;
+        if (act && ib + quota < w.nb) prop = __ldg(&p.blk[w.bbase + ib + quota].x);
+    }
     return prop;
 }
 
@@ -113,7 +169,7 @@ __device__ __forceinline__ ChunkPlan plan_chunk(const SearchParams &p, WarpState
     // a term whose next posting is known to lie at or past the window end has nothing in this chunk: do not load it
     // again (sparse terms next to dense ones would otherwise re-load the same block for thousands of chunks)
     if (act && !(hi != INF && w.next_doc >= hi)) {
-        uint32_t endp = min((ib + quota) * BM25X_BLOCK, w.dfj);
+        const uint32_t endp = min(C::EXACTQ ? c.gsrc + quota * BM25X_BLOCK : (ib + quota) * BM25X_BLOCK, w.dfj);
         c.len = (endp - c.gsrc + 1u) & ~1u;  // whole 16-byte units; an odd tail is the term's pad slot
     }
     uint32_t incl = c.len;
@@ -470,8 +526,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_wq(const __grid_consta
                     if (keep && p.allow && !((p.allow[doc >> 3] >> (doc & 7u)) & 1u)) keep = false;
                     // a posting whose tag won its slot although other runs hold the document: its twin carries it
                     // (only runs that are streamed take part in the tag map: probed terms do not make a twin)
-                    if (keep && cnt_streamed > 1 && (ent >> 31) == 0 &&
-                        map[slot_of<C::LOG_S>(doc)] == (uint8_t)(((ent >> 16) & 0x7FFFu) + 1u))
+                    if (keep && cnt_streamed > 1 && (ent >> 31) == 0 && tag_intact<C>(map, doc, ((ent >> 16) & 0x7FFFu) + 1u))
                         keep = false;
                     keep = keep && (!f.tv || Sx > f.Sk || (Sx == f.Sk && doc < f.dk));
                     const uint32_t mk = __ballot_sync(0xFFFFFFFFu, keep);
@@ -516,10 +571,10 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_wq(const __grid_consta
 #pragma unroll
                             for (int u = 0; u < C::AU; ++u) dd[u] = st[i + 32u * u].doc;
 #pragma unroll
-                            for (int u = 0; u < C::AU; ++u) map[slot_of<C::LOG_S>(dd[u])] = tagv;
+                            for (int u = 0; u < C::AU; ++u) tag_mark<C>(map, dd[u], tagv);
                         }
                     }
-                    for (; i < e; i += 32) map[slot_of<C::LOG_S>(st[i].doc)] = tagv;
+                    for (; i < e; i += 32) tag_mark<C>(map, st[i].doc, tagv);
                 }
                 __syncwarp();
             }
@@ -541,8 +596,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_wq(const __grid_consta
                     bool anyd = false, anyg = false;
 #pragma unroll
                     for (int u = 0; u < C::BU; ++u) {
-                        const uint32_t t = multi ? (uint32_t)map[slot_of<C::LOG_S>(pp[u].doc)] : tagv;
-                        dd[u] = vv[u] && t != tagv;
+                        dd[u] = vv[u] && multi && !tag_intact<C>(map, pp[u].doc, tagv);
                         // threshold test in the tf domain (no division), unconditional: no branches; the signature
                         // tie rule is only evaluated for the few postings that get this far
                         const float r = ctf * s1f[pp[u].w & 0xFFu];
@@ -587,7 +641,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_wq(const __grid_consta
                     const Posting v = st[ent & 0xFFFFu];
                     const unsigned long long key = has ? (unsigned long long)v.doc : ((1ull << 32) | (unsigned)lane);
                     const uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);
-                    const uint32_t winner = has ? (uint32_t)map[slot_of<C::LOG_S>(v.doc)] - 1u : 0u;
+                    const uint32_t winner = has ? tag_winner<C>(map, v.doc) : 0u;
                     const float Fm = score_f32(v.w, __shfl_sync(0xFFFFFFFFu, w.s0f, j & 31u), s1f);
                     float F = 0.f;
                     uint32_t cnt = 0, rem = peers;
@@ -617,7 +671,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_wq(const __grid_consta
                     const uint32_t ent = has ? dupl[base + lane] : 0u;
                     const uint32_t j = ent >> 16;
                     const Posting v = st[ent & 0xFFFFu];
-                    const uint32_t winner = (uint32_t)map[slot_of<C::LOG_S>(v.doc)] - 1u;
+                    const uint32_t winner = tag_winner<C>(map, v.doc);
                     float F = 0.f;
                     uint32_t cnt = 0;
                     bool owner = has;
