@@ -41,6 +41,12 @@ namespace {
 #ifndef BM25X_EXACTQ
 #define BM25X_EXACTQ 1
 #endif
+#ifndef BM25X_LAZYCUT
+#define BM25X_LAZYCUT 1
+#endif
+#ifndef BM25X_MAXWARPS
+#define BM25X_MAXWARPS 16
+#endif
 
 template <int M_, int KP_>
 struct WCfg {
@@ -48,8 +54,8 @@ struct WCfg {
     static constexpr int KP = KP_;                  // pool capacity (power of two >= k + LCAP)
     // block budget per chunk (Σ quota = CB exactly): two 128-posting blocks per term for m = M <= 4
     static constexpr int CB = BM25X_CBMUL * M_;
-    // tag map bytes: queries of 5+ terms unite many more postings per window and see far more slot collisions
-    static constexpr int LOG_S = BM25X_LOG_S > 0 ? BM25X_LOG_S : (M_ > 4 ? 13 : 12);
+    // tag map bytes: queries of 4+ terms unite 1000+ postings per window and see far more slot collisions
+    static constexpr int LOG_S = BM25X_LOG_S > 0 ? BM25X_LOG_S : (M_ >= 4 ? 13 : 12);
     static constexpr int SUB_TARGET = LOG_S >= 12 ? (BM25X_SUBT << (LOG_S - 12)) : (BM25X_SUBT >> (12 - LOG_S));  // postings per tag-map sub-window (classes with more than 4 terms)
     static constexpr int NSTG = 1;                  // stages per warp: 1 = rely on the other warps to hide the load latency
     static constexpr int LCAP = 64;                 // candidate / possible-duplicate list entries
@@ -58,8 +64,9 @@ struct WCfg {
     static constexpr int NSUB_SMALL = BM25X_NSUB_SMALL;  // sub-windows per chunk for classes up to 4 terms
     // Two half-size tag maps under independent hashes instead of one: a posting is a possible duplicate only when its
     // tag lost BOTH slots (a later run holding the same document overwrites both), which squares the false-alarm rate
-    // (pays for its extra hash + byte load per posting only where collisions are frequent: the 5+ term classes)
-    static constexpr bool TWOMAP = BM25X_TWOMAP >= 0 ? BM25X_TWOMAP != 0 : (M_ > 4);
+    // (pays for its extra hash + byte load per posting only where collisions are frequent: the 4+ term classes;
+    // measured: 3-term queries 22.8 ms single / 24.5 ms double, 1..8-term mix 66 ms single / 56 ms double)
+    static constexpr bool TWOMAP = BM25X_TWOMAP >= 0 ? BM25X_TWOMAP != 0 : (M_ >= 4);
     static constexpr int LOG_M = TWOMAP ? LOG_S - 1 : LOG_S;
     // Loads of exactly quota*128 postings from where the last window ended (window end = doc id of the first posting
     // not loaded, one 4-byte read) instead of loads ending on block boundaries: no half-used blocks in the stage
@@ -79,8 +86,9 @@ struct WCfg {
     static constexpr size_t warp_bytes = (off_bar + 8 * NSTG + 127) & ~(size_t)127;
     static constexpr size_t off_s1f = 0;  // CTA-shared: 1 KiB table first, then the warps
     static constexpr size_t shared_bytes = 1024;
-    static constexpr int WARPS = (int)((227 * 1024 - shared_bytes) / warp_bytes) > 16 ? 16
-                                 : (int)((227 * 1024 - shared_bytes) / warp_bytes);
+    static constexpr int WARPS = (int)((227 * 1024 - shared_bytes) / warp_bytes) > BM25X_MAXWARPS
+                                     ? BM25X_MAXWARPS
+                                     : (int)((227 * 1024 - shared_bytes) / warp_bytes);
     static constexpr size_t total = shared_bytes + warp_bytes * WARPS;
     static constexpr int THREADS = WARPS * 32;
 };
@@ -538,7 +546,10 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_wq(const __grid_consta
                     }
                     pn += __popc(mk);
                     __syncwarp();
-                    if (pn > C::KP - 32 || pn >= (int)k + 32) pool_cut();
+                    // Re-sorting the pool is the expensive part of a large k (bitonic sort of KP entries): once a
+                    // threshold exists, the big pool is cut only when it is about to overflow.
+                    const bool lazy = BM25X_LAZYCUT && C::KP > 128 && f.tv;
+                    if (pn > C::KP - 32 || (!lazy && pn >= (int)k + 32)) pool_cut();
                 }
                 nc = 0;
             };
