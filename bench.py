@@ -93,15 +93,24 @@ class ClockSampler:
 
 
 def measured_traffic(workload, nq, k):
-    """dram__bytes_read.sum + dram__bytes_write.sum of the search kernel from the committed `ncu --set full` capture
-    of this exact launch (profiles/r1_final_traffic.json), else None."""
-    try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r1_final_traffic.json")))
-        if t["workload"] == workload and t["queries"] == nq and t["k"] == k:
-            return t["dram_bytes_read"] + t["dram_bytes_write"]
-    except Exception:
-        pass
+    """dram__bytes_read.sum + dram__bytes_write.sum of the search kernel from the committed ncu capture of this exact
+    launch (profiles/r1b_traffic.json — newest kernel first), else None."""
+    for name in ("r1b_traffic.json",):
+        try:
+            t = json.load(open(os.path.join(ROOT, "profiles", name)))
+            if t["workload"] == workload and t["queries"] == nq and t["k"] == k:
+                return t["dram_bytes_read"] + t["dram_bytes_write"]
+        except Exception:
+            pass
     return None
+
+
+def kernel_name(tmax, k):
+    """The kernel instance the library launches for the widest query class of the workload (bm25x_search.cu)."""
+    cls = next(c for c in (1, 2, 3, 4, 8, 16, 32) if c >= tmax)
+    if k <= 128 and cls <= 8:
+        return f"k_search_wq<WCfg<{cls},{128 if k <= 32 else 256}>>"
+    return f"k_search<KCfg<{cls}>>"
 
 
 def hbm_peak():
@@ -329,7 +338,7 @@ def main():
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 filter + f64 exact re-score (u32 doc ids)", "data": "synthetic", "config": config,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None if a.no_prune else measured_traffic(a.workload, nq, k), "peak_source": peak_src, "kernel": f"k_search<M={wl['tmax']}>",
+                         "traffic": None if a.no_prune else measured_traffic(a.workload, nq, k), "peak_source": peak_src, "kernel": kernel_name(wl["tmax"], k),
                          "kernel_ms": kms, "algorithmic_bytes_per_launch": bytes_algo,
                          "postings_exhaustive": int(st.postings), "postings_streamed": fetched,
                          "pruning": "off" if a.no_prune else "on",
