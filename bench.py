@@ -198,6 +198,8 @@ def main():
               "zipf_s": wl["zipf"], "postings": n_postings,
               "parallelism": f"queries sharded over {world} GPU(s), index replicated (NCCL broadcast at load)",
               "l2": "index (8 B/posting) is far larger than the 126 MB L2; no flush needed",
+              "k_note": "BASELINE.json's metric says top-10, its configs[2] words the same 10M-doc case as top-100: "
+                        "`value` is top-10, the `top100` object is the same batch at k=100",
               "gen_s": round(t_gen, 1), "index_build_s": round(t_index, 1), "replicate_s": round(t_repl, 2)}
 
     if a.impl == "reference":

@@ -83,3 +83,45 @@ def test_document_query_types(m):
         m.Document([1, 2], [1, 0])      # tf == 0
     with pytest.raises(ValueError):
         m.Query([3, 3])
+
+
+def test_struct_layouts_match_the_header(m):
+    """The ctypes mirrors in bm25x.py (the stand-in for the Rust #[repr(C)] structs of INTEGRATION.md) must have the
+    sizes and field offsets the C compiler gives include/bm25x.h."""
+    import ctypes as C
+    import subprocess
+    import tempfile
+
+    bm = __import__(m.__name__ + ".bm25x", fromlist=["x"])
+    HEADER = os.path.join(ROOT, "include", "bm25x.h")
+    structs = {"bm25x_corpus": (bm._Corpus, ["n_docs", "doc_len", "payload", "n_terms", "term_key", "post_off",
+                                             "post_doc", "post_tf", "k1", "b"]),
+               "bm25x_blocks": (bm._Blocks, ["n_docs", "doc_len", "doc_fieldnorm", "sum_doc_len", "payload", "n_terms",
+                                             "term_key", "term_blk_off", "n_blocks", "blk_min_doc", "blk_n",
+                                             "blk_meta_doc", "blk_meta_tf", "blk_doc_off", "blk_tf_off", "bytes",
+                                             "n_bytes", "k1", "b"]),
+               "bm25x_index_info": (bm.IndexInfo, ["n_docs", "n_terms", "n_postings", "sum_doc_len", "avgdl", "k1", "b",
+                                                   "device_bytes", "n_blocks", "device"]),
+               "bm25x_index_layout": (bm.IndexLayout, ["n_docs", "n_terms", "n_postings", "n_postings_padded",
+                                                       "n_blocks", "sum_doc_len", "k1", "b", "avgdl", "dev_ptr",
+                                                       "bytes", "device"]),
+               "bm25x_search_stats": (bm.SearchStats, ["kernel_ms", "h2d_ms", "d2h_ms", "postings", "bytes_algo",
+                                                       "launches", "queries", "postings_fetched"])}
+    prog = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', 'int main(void) {']
+    for cname, (_, fields) in structs.items():
+        prog.append(f'printf("{cname} %zu", sizeof({cname}));')
+        for f in fields:
+            prog.append(f'printf(" %zu", offsetof({cname}, {f}));')
+        prog.append('printf("\\n");')
+    prog.append('return 0; }')
+    with tempfile.TemporaryDirectory() as d:
+        src, exe = os.path.join(d, "layout.c"), os.path.join(d, "layout")
+        open(src, "w").write("\n".join(prog))
+        subprocess.check_call(["gcc", "-std=c11", "-o", exe, src])
+        out = subprocess.check_output([exe], text=True)
+    for line in out.splitlines():
+        name, size, *offs = line.split()
+        cls, fields = structs[name]
+        assert C.sizeof(cls) == int(size), f"{name}: ctypes size {C.sizeof(cls)} != C {size}"
+        assert [f for f, _ in cls._fields_] == fields, f"{name}: field order"
+        assert [getattr(cls, f).offset for f in fields] == [int(o) for o in offs], f"{name}: field offsets"

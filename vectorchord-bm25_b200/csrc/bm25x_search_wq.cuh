@@ -44,6 +44,9 @@ namespace {
 #ifndef BM25X_LAZYCUT
 #define BM25X_LAZYCUT 1
 #endif
+#ifndef BM25X_BALANCED
+#define BM25X_BALANCED 0
+#endif
 #ifndef BM25X_MAXWARPS
 #define BM25X_MAXWARPS 16
 #endif
@@ -348,7 +351,19 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_wq(const __grid_consta
             const uint32_t extra = (uint32_t)C::CB - w.m;
             const uint32_t share = lane < (int)w.m ? (uint32_t)(((uint64_t)extra * w.dfj) / sumdf) : 0u;
             const uint32_t left = extra - __reduce_add_sync(0xFFFFFFFFu, share);
+#if BM25X_BALANCED
+            // largest-remainder split: the leftover blocks go to the terms that lost most by the flooring, so equally
+            // frequent terms get equal loads (not yet the default: unmeasured, see DESIGN.md §4.1 "known inefficiency")
+            const uint64_t rem = lane < (int)w.m ? ((uint64_t)extra * w.dfj) % sumdf : 0ull;
+            uint32_t rank = 0;
+            for (uint32_t i = 0; i < w.m; ++i) {
+                const uint64_t ri = __shfl_sync(0xFFFFFFFFu, rem, i);
+                rank += (ri > rem || (ri == rem && (int)i < lane)) ? 1u : 0u;
+            }
+            w.quota_full = lane < (int)w.m ? 1u + share + (rank < left ? 1u : 0u) : 0u;
+#else
             w.quota_full = lane < (int)w.m ? 1u + share + (lane < (int)left ? 1u : 0u) : 0u;
+#endif
         }
         w.gpos = 0;
         w.next_doc = 0;
