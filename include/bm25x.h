@@ -164,6 +164,42 @@ int bm25x_batch_fetch(bm25x_batch *batch, uint32_t *out_doc, float *out_score, d
                       uint16_t *out_payload, uint32_t *out_n);
 void bm25x_batch_destroy(bm25x_batch *batch);
 
+/* ---- the growing segment: documents inserted since the last seal.  bm25::search scans them one by one
+ * before it walks the sealed postings (crates/bm25/src/search.rs:83-135): every non-deleted growing document is scored
+ * over the query tokens that exist in the SEALED segment with the sealed statistics — Cache::new(sealed N, sealed df,
+ * k1, b, sealed avgdl) (search.rs:49-51,66-77; `insert` does not update them) — and shares the Results heap with the
+ * sealed documents.  Here the growing documents are inverted once into a second, small index handle that carries
+ * the sealed statistics, so the same kernels unite their postings; a query then is two top-k searches + a merge.
+ * Doc ids of the growing handle are growing ordinals (insertion order).  Re-create the handle after inserts/deletes
+ * (it is as cheap as the segment is small); `maintain`/seal = build a new sealed index. */
+typedef struct {
+    uint32_t n_docs;               /* growing documents, in VectorTuple-chain order */
+    const uint32_t *doc_len;       /* [n_docs] exact lengths, or NULL: then doc_fieldnorm */
+    const uint8_t *doc_fieldnorm;  /* [n_docs] VectorTuple fieldnorm (search.rs:96-98); used when doc_len == NULL */
+    const uint16_t *payload;       /* [n_docs*3] VectorTuple.payload (ctid), or NULL */
+    const uint8_t *deleted;        /* [n_docs] VectorTuple.deleted (search.rs:110): non-zero = skipped; or NULL */
+    const uint64_t *elem_off;      /* [n_docs+1] */
+    const uint32_t *elem_term;     /* Element.key as term ordinal of the SEALED index (bm25x_lookup_terms), strictly
+                                      ascending inside a document; BM25X_TERM_MISSING = token unknown to the sealed
+                                      segment: it can never match a query token (search.rs:60-62) */
+    const uint32_t *elem_tf;       /* Element.value, != 0 */
+} bm25x_growing_docs;
+int bm25x_growing_create(const bm25x_index *sealed, const bm25x_growing_docs *docs, bm25x_index **out);
+/* bm25::search over sealed + growing: bm25x_search_batch on both handles and the merge below.  `growing` may be NULL
+ * (sealed only).  Doc ids >= n_docs(sealed) denote growing ordinal (id - n_docs(sealed)); on equal scores sealed
+ * documents come first, then ascending id (the reference's order of equal scores is not pinned, see bm25x_search_batch).
+ * allow_growing: optional prefilter bitmap over growing ordinals. */
+int bm25x_search_batch_growing(bm25x_index *sealed, bm25x_index *growing, uint32_t nq, const uint32_t *q_off,
+                               const uint32_t *q_terms, uint32_t k, const uint8_t *allow_sealed,
+                               const uint8_t *allow_growing, uint32_t *out_doc, float *out_score, double *out_score64,
+                               uint16_t *out_payload, uint32_t *out_n, bm25x_search_stats *stats);
+/* Host-only: row-wise merge of two top-k result sets (score desc; equal scores: list a first, then ascending id);
+ * ids of list b are shifted by doc_base_b.  f64 scores of both lists are required; f32 scores / payloads optional. */
+int bm25x_merge_topk(uint32_t nq, uint32_t k, const uint32_t *doc_a, const float *score_a, const double *score64_a,
+                     const uint16_t *payload_a, const uint32_t *n_a, const uint32_t *doc_b, const float *score_b,
+                     const double *score64_b, const uint16_t *payload_b, const uint32_t *n_b, uint32_t doc_base_b,
+                     uint32_t *out_doc, float *out_score, double *out_score64, uint16_t *out_payload, uint32_t *out_n);
+
 /* ---- bm25::evaluate (crates/bm25/src/evaluate.rs:22-74) behind `<&>` without an index scan
  * (src/index/operators.rs:22-55): pair p scores document [d_off[p], d_off[p+1]) (sorted distinct term ordinals
  * with tfs) against query [q_off[p], q_off[p+1]) (sorted distinct ordinals).  out[p] = positive f64 score. */

@@ -877,6 +877,59 @@ double orc_evaluate(const orc_index *ix, const uint32_t *doc_terms, const uint32
 }
 
 /* ------------------------------------------------------------------------- */
+/* Growing segment (search.rs:83-135): the documents inserted since the last seal are scanned one by one; each is
+ * scored with the SEALED segment's statistics — Cache::new(number_of_documents, token.number_of_documents, k1, b,
+ * avgdl) of the sealed JumpTuple/TokenTuple (search.rs:49-51,66-77) — over the query tokens that exist in the sealed
+ * segment (others are dropped, search.rs:60-62), elements in ascending key order (search.rs:112-118), deleted
+ * documents skipped (search.rs:110), pushed only when `threshold() < result` with the initial threshold 0.0
+ * (search.rs:81,119).  Exhaustive + canonical order (score desc, growing ordinal asc), like orc_search_exhaustive.
+ * Document g: elements elem_term/elem_tf[elem_off[g] .. elem_off[g+1]) (term ordinals ascending; ordinals unknown to
+ * the sealed segment, e.g. 0xFFFFFFFF, never match), norm fieldnorm[g]. */
+int orc_search_growing(const orc_index *ix, uint32_t n_growing, const uint8_t *fieldnorm, const uint8_t *deleted,
+                       const uint64_t *elem_off, const uint32_t *elem_term, const uint32_t *elem_tf,
+                       const uint32_t *terms, int nterms, int k, const uint8_t *allow, uint32_t *out_doc,
+                       double *out_score) {
+    if (k <= 0 || nterms <= 0) return 0;
+    uint32_t *q = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)nterms);
+    const int m = canon_query(ix, terms, nterms, q); /* tokens found in the sealed segment, ascending */
+    double *s0 = (double *)malloc(sizeof(double) * (size_t)(m ? m : 1));
+    double s1[256], dummy;
+    orc_cache_new(ix->n_docs, 1, ix->k1, ix->b, ix->avgdl, &dummy, s1);
+    for (int j = 0; j < m; j++) s0[j] = orc_idf(ix->n_docs, ix->df[q[j]]) * (ix->k1 + 1.0);
+    sd_t *cand = (sd_t *)malloc(sizeof(sd_t) * (n_growing ? n_growing : 1));
+    uint64_t nc = 0;
+    for (uint32_t g = 0; g < n_growing && m > 0; g++) {
+        if (deleted && deleted[g]) continue;
+        double result = 0.0;
+        for (uint64_t e = elem_off[g]; e < elem_off[g + 1]; e++) {
+            /* tokens.binary_search_by_key(&key) */
+            int lo = 0, hi = m;
+            while (lo < hi) {
+                int mid = (lo + hi) >> 1;
+                if (q[mid] < elem_term[e]) lo = mid + 1;
+                else hi = mid;
+            }
+            if (lo < m && q[lo] == elem_term[e]) result += orc_cache_evaluate(s0[lo], s1, fieldnorm[g], elem_tf[e]);
+        }
+        if (!(0.0 < result)) continue; /* results.threshold() < result */
+        if (allow && !(allow[g >> 3] >> (g & 7) & 1)) continue;
+        cand[nc].d = g;
+        cand[nc].s = result;
+        nc++;
+    }
+    qsort(cand, (size_t)nc, sizeof(sd_t), sd_cmp);
+    const int n = nc < (uint64_t)k ? (int)nc : k;
+    for (int i = 0; i < n; i++) {
+        out_doc[i] = cand[i].d;
+        out_score[i] = cand[i].s;
+    }
+    free(cand);
+    free(s0);
+    free(q);
+    return n;
+}
+
+/* ------------------------------------------------------------------------- */
 /* Synthetic corpus spec (mirrors tests/fuzz:168-205: L draws with
  * replacement, duplicates aggregated into tf, doc length = L).  Counter-based
  * so any doc can be regenerated independently on CPU or GPU. */

@@ -100,6 +100,13 @@ void orc_search_exhaustive_batch(const orc_index *idx, int nq, const uint32_t *q
 double orc_evaluate(const orc_index *idx, const uint32_t *doc_terms, const uint32_t *doc_tfs,
                     int doc_n, const uint32_t *query_terms, int query_n);
 
+/* Growing segment scan (search.rs:83-135) against the sealed index `idx`: exhaustive, canonical order; doc ids are
+ * growing ordinals.  Returns the number of results (<= k). */
+int orc_search_growing(const orc_index *idx, uint32_t n_growing, const uint8_t *fieldnorm, const uint8_t *deleted,
+                       const uint64_t *elem_off, const uint32_t *elem_term, const uint32_t *elem_tf,
+                       const uint32_t *terms, int nterms, int k, const uint8_t *allow, uint32_t *out_doc,
+                       double *out_score);
+
 /* ---- synthetic corpus spec (ours; mirrors tests/fuzz:168-205) ---- */
 uint64_t orc_splitmix64(uint64_t x);
 /* Build the integer inverse-CDF thresholds for Zipf(s) over `vocab` ranks

@@ -90,6 +90,9 @@ def lib():
     L.orc_draw_term.argtypes = [C.c_uint64, C.c_uint32, u64p]
     L.orc_synth_doc.restype = C.c_int
     L.orc_synth_doc.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, u64p, u32p, u32p, u32p]
+    L.orc_search_growing.restype = C.c_int
+    L.orc_search_growing.argtypes = [C.c_void_p, C.c_uint32, u8p, u8p, u64p, u32p, u32p, u32p, C.c_int, C.c_int, u8p,
+                                     u32p, f64p]
     L.orc_compress_document_ids.restype = C.c_uint32
     L.orc_compress_document_ids.argtypes = [C.c_uint32, u32p, C.c_uint32, u8p, u8p]
     L.orc_decompress_document_ids.restype = C.c_uint32
@@ -238,6 +241,19 @@ class OracleIndex:
                                               nthreads, _p(od, C.c_uint32), _p(os_, C.c_double), _p(on, C.c_uint32))
         return od, os_, on, st
 
+    def search_growing(self, g: "GrowingDocs", terms, k, allow=None):
+        """The growing-segment scan of bm25::search (search.rs:83-135) against this sealed index: exhaustive,
+        canonical order; ids are growing ordinals."""
+        terms = _u32(terms)
+        out_d = np.zeros(max(k, 1), dtype=np.uint32)
+        out_s = np.zeros(max(k, 1), dtype=np.float64)
+        al = np.ascontiguousarray(allow, dtype=np.uint8) if allow is not None else None
+        n = lib().orc_search_growing(self.h, g.n_docs, _p(g.fieldnorm, C.c_uint8), _p(g.deleted, C.c_uint8),
+                                     _p(g.elem_off, C.c_uint64), _p(g.elem_term, C.c_uint32),
+                                     _p(g.elem_tf, C.c_uint32), _p(terms, C.c_uint32), len(terms), int(k),
+                                     _p(al, C.c_uint8), _p(out_d, C.c_uint32), _p(out_s, C.c_double))
+        return out_d[:n].copy(), out_s[:n].copy()
+
     def evaluate(self, doc_terms, doc_tfs, query_terms):
         dt, df_, qt = _u32(doc_terms), _u32(doc_tfs), _u32(query_terms)
         return lib().orc_evaluate(self.h, _p(dt, C.c_uint32), _p(df_, C.c_uint32), len(dt), _p(qt, C.c_uint32),
@@ -334,3 +350,27 @@ class EncodedBlocks:
         assert got == n_bytes and int(self.term_blk_off[T]) == nb
         self.n_blocks = nb
         self.n_bytes = int(n_bytes)
+
+
+class GrowingDocs:
+    """Documents inserted since the last seal (the VectorTuple chain of search.rs:83-135), doc-major: document g holds
+    (term ordinal, tf) elements elem_off[g]..elem_off[g+1], ascending terms; norms quantised like flush.rs:58."""
+
+    def __init__(self, elem_off, elem_term, elem_tf, doc_len, deleted=None):
+        self.elem_off = np.ascontiguousarray(elem_off, dtype=np.uint64)
+        self.elem_term = _u32(elem_term)
+        self.elem_tf = _u32(elem_tf)
+        self.doc_len = _u32(doc_len)
+        self.n_docs = len(self.elem_off) - 1
+        self.fieldnorm = np.array([lib().orc_length_to_fieldnorm(int(x)) for x in self.doc_len], dtype=np.uint8)
+        self.deleted = np.ascontiguousarray(deleted, dtype=np.uint8) if deleted is not None else None
+
+    @staticmethod
+    def from_corpus(c: "Corpus", deleted=None):
+        """Transpose a term-major corpus into its documents."""
+        df = (c.post_off[1:] - c.post_off[:-1]).astype(np.int64)
+        term = np.repeat(np.arange(c.n_terms, dtype=np.uint32), df)
+        order = np.lexsort((term, c.post_doc))
+        cnt = np.bincount(c.post_doc, minlength=c.n_docs).astype(np.uint64)
+        off = np.concatenate([[0], np.cumsum(cnt)]).astype(np.uint64)
+        return GrowingDocs(off, term[order], c.post_tf[order], c.doc_len, deleted)

@@ -6,7 +6,7 @@ host-side interface for the path (`bm25::search` / `bm25::evaluate`, Document / 
 falls back to a CPU implementation: if the library or a B200 is missing, calls raise.
 """
 from .bm25x import (Bm25xError, Index, Batch, SearchStats, IndexLayout, synth_corpus, synth_queries, load_library, build_library,
-                    device_count, Document, Query, MAX_K, MAX_QUERY_TERMS, TERM_MISSING)
+                    device_count, Document, Query, MAX_K, MAX_QUERY_TERMS, TERM_MISSING, merge_topk)
 
 __all__ = ["Bm25xError", "Index", "Batch", "SearchStats", "IndexLayout", "synth_corpus", "synth_queries", "load_library",
-           "build_library", "device_count", "Document", "Query", "MAX_K", "MAX_QUERY_TERMS", "TERM_MISSING"]
+           "build_library", "device_count", "Document", "Query", "MAX_K", "MAX_QUERY_TERMS", "TERM_MISSING", "merge_topk"]

@@ -39,6 +39,13 @@ class _Blocks(C.Structure):
                 ("bytes", C.POINTER(C.c_uint8)), ("n_bytes", C.c_uint64), ("k1", C.c_double), ("b", C.c_double)]
 
 
+class _GrowingDocs(C.Structure):
+    _fields_ = [("n_docs", C.c_uint32), ("doc_len", C.POINTER(C.c_uint32)), ("doc_fieldnorm", C.POINTER(C.c_uint8)),
+                ("payload", C.POINTER(C.c_uint16)), ("deleted", C.POINTER(C.c_uint8)),
+                ("elem_off", C.POINTER(C.c_uint64)), ("elem_term", C.POINTER(C.c_uint32)),
+                ("elem_tf", C.POINTER(C.c_uint32))]
+
+
 class IndexInfo(C.Structure):
     _fields_ = [("n_docs", C.c_uint32), ("n_terms", C.c_uint32), ("n_postings", C.c_uint64),
                 ("sum_doc_len", C.c_uint64), ("avgdl", C.c_double), ("k1", C.c_double), ("b", C.c_double),
@@ -92,6 +99,11 @@ def load_library():
                                              C.POINTER(C.c_double))
     L.bm25x_index_create.argtypes = [C.POINTER(_Corpus), C.c_int, C.POINTER(vp)]
     L.bm25x_index_create_from_blocks.argtypes = [C.POINTER(_Blocks), C.c_int, C.POINTER(vp)]
+    L.bm25x_growing_create.argtypes = [vp, C.POINTER(_GrowingDocs), C.POINTER(vp)]
+    L.bm25x_search_batch_growing.argtypes = [vp, vp, C.c_uint32, u32p, u32p, C.c_uint32, u8p, u8p, u32p, f32p, f64p,
+                                             u16p, u32p, C.POINTER(SearchStats)]
+    L.bm25x_merge_topk.argtypes = [C.c_uint32, C.c_uint32, u32p, f32p, f64p, u16p, u32p, u32p, f32p, f64p, u16p, u32p,
+                                   C.c_uint32, u32p, f32p, f64p, u16p, u32p]
     L.bm25x_index_destroy.argtypes = [vp]
     L.bm25x_index_destroy.restype = None
     L.bm25x_index_get_info.argtypes = [vp, C.POINTER(IndexInfo)]
@@ -351,6 +363,55 @@ class Index:
         n = int(r["n"][0])
         return r["doc"][0, :n].copy(), r["score64"][0, :n].copy()
 
+    # ---- growing segment (documents inserted since the last seal; search.rs:83-135) ----
+    def growing(self, elem_off, elem_term, elem_tf, doc_len=None, doc_fieldnorm=None, payload=None,
+                deleted=None) -> "Index":
+        """Handle over the growing documents (doc-major: document g holds elements elem_off[g]..elem_off[g+1], term
+        ordinals of THIS sealed index ascending, TERM_MISSING for tokens it does not know) that scores with this
+        index's statistics (bm25x_growing_create).  Search it like any index; ids are growing ordinals."""
+        g = _GrowingDocs()
+        keep = []
+
+        def arr(a, dt, ct):
+            a = np.ascontiguousarray(a, dtype=dt)
+            keep.append(a)
+            return _p(a, ct)
+
+        g.elem_off = arr(elem_off, np.uint64, C.c_uint64)
+        g.n_docs = len(keep[-1]) - 1
+        g.elem_term = arr(elem_term, np.uint32, C.c_uint32)
+        g.elem_tf = arr(elem_tf, np.uint32, C.c_uint32)
+        if doc_len is not None:
+            g.doc_len = arr(doc_len, np.uint32, C.c_uint32)
+        if doc_fieldnorm is not None:
+            g.doc_fieldnorm = arr(doc_fieldnorm, np.uint8, C.c_uint8)
+        if payload is not None:
+            g.payload = arr(payload, np.uint16, C.c_uint16)
+        if deleted is not None:
+            g.deleted = arr(deleted, np.uint8, C.c_uint8)
+        h = C.c_void_p()
+        _check(load_library().bm25x_growing_create(self.h, C.byref(g), C.byref(h)))
+        return Index._adopt(h, g.n_docs, self.n_terms)
+
+    def search_batch_growing(self, growing, q_off, q_terms, k, allow=None, allow_growing=None, want_payload=False):
+        """bm25::search over this sealed index + a growing handle (None = sealed only): ids >= n_docs are growing
+        ordinal + n_docs."""
+        q_off = np.ascontiguousarray(q_off, dtype=np.uint32)
+        q_terms = np.ascontiguousarray(q_terms, dtype=np.uint32)
+        nq, kk = len(q_off) - 1, int(k)
+        out = {"doc": np.empty((nq, kk), np.uint32), "score": np.empty((nq, kk), np.float32),
+               "score64": np.empty((nq, kk), np.float64),
+               "payload": np.empty((nq, kk, 3), np.uint16) if want_payload else None, "n": np.empty(nq, np.uint32)}
+        al = np.ascontiguousarray(allow, dtype=np.uint8) if allow is not None else None
+        alg = np.ascontiguousarray(allow_growing, dtype=np.uint8) if allow_growing is not None else None
+        st = SearchStats()
+        _check(load_library().bm25x_search_batch_growing(
+            self.h, growing.h if growing is not None else None, nq, _p(q_off, C.c_uint32), _p(q_terms, C.c_uint32), kk,
+            _p(al, C.c_uint8), _p(alg, C.c_uint8), _p(out["doc"], C.c_uint32), _p(out["score"], C.c_float),
+            _p(out["score64"], C.c_double), _p(out["payload"], C.c_uint16), _p(out["n"], C.c_uint32), C.byref(st)))
+        out["stats"] = st
+        return out
+
     def prepare(self, q_off, q_terms, k, allow=None) -> "Batch":
         return Batch(self, q_off, q_terms, k, allow)
 
@@ -371,6 +432,28 @@ class Index:
 
     def evaluate(self, document: Document, query: Query) -> float:
         return float(self.evaluate_batch([document], [query])[0])
+
+
+def merge_topk(a, b, doc_base_b, k):
+    """Host-only bm25x_merge_topk of two result dicts (as returned by search_batch with f64 scores)."""
+    nq = len(a["n"])
+    assert a["doc"].shape == (nq, k) and b["doc"].shape == (nq, k)
+    pay = a.get("payload") is not None and b.get("payload") is not None
+    out = {"doc": np.empty((nq, k), np.uint32), "score": np.empty((nq, k), np.float32),
+           "score64": np.empty((nq, k), np.float64), "payload": np.empty((nq, k, 3), np.uint16) if pay else None,
+           "n": np.empty(nq, np.uint32)}
+    c = lambda x, dt: np.ascontiguousarray(x, dtype=dt)
+    keep = [c(a["doc"], np.uint32), c(a["score"], np.float32), c(a["score64"], np.float64),
+            c(a["payload"], np.uint16) if pay else None, c(a["n"], np.uint32),
+            c(b["doc"], np.uint32), c(b["score"], np.float32), c(b["score64"], np.float64),
+            c(b["payload"], np.uint16) if pay else None, c(b["n"], np.uint32)]
+    ty = [C.c_uint32, C.c_float, C.c_double, C.c_uint16, C.c_uint32] * 2
+    _check(load_library().bm25x_merge_topk(nq, int(k), *[_p(x, t) for x, t in zip(keep[:5], ty[:5])],
+                                           *[_p(x, t) for x, t in zip(keep[5:], ty[5:])], int(doc_base_b),
+                                           _p(out["doc"], C.c_uint32), _p(out["score"], C.c_float),
+                                           _p(out["score64"], C.c_double), _p(out["payload"], C.c_uint16),
+                                           _p(out["n"], C.c_uint32)))
+    return out
 
 
 class Batch:

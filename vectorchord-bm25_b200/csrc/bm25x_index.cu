@@ -189,6 +189,10 @@ struct BuildMeta {
     uint64_t n_post;
     const uint8_t *fieldnorm = nullptr;  // when doc_len == NULL: DocumentTuple.fieldnorm per doc + JumpTuple.sum_of_document_lengths
     uint64_t sum_len = 0;
+    // growing segment (search.rs:66-77): score with the SEALED segment's statistics instead of the index's own
+    const uint32_t *stat_df = nullptr;  // [n_terms] sealed TokenTuple.number_of_documents
+    uint32_t stat_n_docs = 0;           // sealed JumpTuple.number_of_documents
+    double stat_avgdl = 0.0;            // sealed sum_of_document_lengths / number_of_documents
 };
 
 static int check_common(const char *who, uint32_t n_docs, const void *doc_len, double k1, double b, int device) {
@@ -262,7 +266,7 @@ static int index_begin(const BuildMeta &m, int device, bm25x_index **ixp) {
         sum_len = m.sum_len;
     }
     ix->sum_len = sum_len;
-    ix->avgdl = (double)sum_len / (double)N;
+    ix->avgdl = m.stat_df ? m.stat_avgdl : (double)sum_len / (double)N;
 
     // ---- per-term df, padded offsets, block offsets, s0 (bm25.rs:285-289,348) ----
     ix->h_df.resize(T);
@@ -277,7 +281,8 @@ static int index_begin(const BuildMeta &m, int device, bm25x_index **ixp) {
         h_blk_off[t] = nb;
         pp += (n + 1) & ~(uint64_t)1;
         nb += (n + BM25X_BLOCK - 1) / BM25X_BLOCK;
-        double idf = log(((double)N + 1.0) / ((double)n + 0.5));
+        const double n_stat = m.stat_df ? (double)m.stat_df[t] : (double)n, N_stat = m.stat_df ? (double)m.stat_n_docs : (double)N;
+        double idf = log((N_stat + 1.0) / (n_stat + 0.5));
         h_s0d[t] = idf * (m.k1 + 1.0);
         h_s0f[t] = (float)h_s0d[t];
     }
@@ -361,6 +366,46 @@ static cudaError_t index_finish_device(bm25x_index *ix) {
     return e;
 }
 
+// Postings of a term-major CSR: chunked H2D of the columns + device transform to the padded AoS, then the derived arrays.
+// Destroys the index on failure.
+static int upload_csr(bm25x_index *ix, const char *who, uint32_t T, uint64_t P, const uint64_t *post_off,
+                      const uint32_t *post_doc, const uint32_t *post_tf) {
+    DeviceIndex &d = ix->d;
+    // ---- postings: chunked H2D of the CSR columns + device transform to the padded AoS ----
+    {
+        uint64_t *d_off = nullptr;
+        uint32_t *d_cdoc = nullptr, *d_ctf = nullptr;
+        const uint64_t CH = 64ull << 20;  // postings per chunk
+        uint64_t chn = std::min<uint64_t>(CH, P ? P : 1);
+        cudaError_t e1 = cudaMalloc((void **)&d_off, sizeof(uint64_t) * ((size_t)T + 1));
+        cudaError_t e2 = cudaMalloc((void **)&d_cdoc, sizeof(uint32_t) * chn);
+        cudaError_t e3 = cudaMalloc((void **)&d_ctf, sizeof(uint32_t) * chn);
+        cudaError_t e = e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3);
+        if (e == cudaSuccess) e = cudaMemcpy(d_off, post_off, sizeof(uint64_t) * ((size_t)T + 1), cudaMemcpyHostToDevice);
+        for (uint64_t base = 0; base < P && e == cudaSuccess; base += CH) {
+            uint64_t n = std::min<uint64_t>(CH, P - base);
+            e = cudaMemcpy(d_cdoc, post_doc + base, sizeof(uint32_t) * n, cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) e = cudaMemcpy(d_ctf, post_tf + base, sizeof(uint32_t) * n, cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) {
+                k_build_postings<<<(unsigned)((n + 255) / 256), 256>>>(d_cdoc, d_ctf, base, n, d_off, d.post_off, T,
+                                                                       d.fieldnorm, d.post);
+                e = cudaGetLastError();
+            }
+            if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        }
+        if (e == cudaSuccess) e = index_finish_device(ix);
+        cudaFree(d_off);
+        cudaFree(d_cdoc);
+        cudaFree(d_ctf);
+        if (e != cudaSuccess) {
+            bm25x_set_error("%s: posting upload failed: %s", who, cudaGetErrorString(e));
+            bm25x_index_destroy(ix);
+            return e == cudaErrorMemoryAllocation ? BM25X_ERR_OOM : BM25X_ERR_CUDA;
+        }
+    }
+    return BM25X_OK;
+}
+
 extern "C" int bm25x_index_create(const bm25x_corpus *c, int device, bm25x_index **out) {
     if (!c || !out) {
         bm25x_set_error("bm25x_index_create: null argument");
@@ -411,40 +456,9 @@ extern "C" int bm25x_index_create(const bm25x_corpus *c, int device, bm25x_index
     bm25x_index *ix = nullptr;
     rc = index_begin(m, device, &ix);
     if (rc != BM25X_OK) return rc;
-    DeviceIndex &d = ix->d;
 
-    // ---- postings: chunked H2D of the CSR columns + device transform to the padded AoS ----
-    {
-        uint64_t *d_off = nullptr;
-        uint32_t *d_cdoc = nullptr, *d_ctf = nullptr;
-        const uint64_t CH = 64ull << 20;  // postings per chunk
-        uint64_t chn = std::min<uint64_t>(CH, P ? P : 1);
-        cudaError_t e1 = cudaMalloc((void **)&d_off, sizeof(uint64_t) * ((size_t)T + 1));
-        cudaError_t e2 = cudaMalloc((void **)&d_cdoc, sizeof(uint32_t) * chn);
-        cudaError_t e3 = cudaMalloc((void **)&d_ctf, sizeof(uint32_t) * chn);
-        cudaError_t e = e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3);
-        if (e == cudaSuccess) e = cudaMemcpy(d_off, c->post_off, sizeof(uint64_t) * ((size_t)T + 1), cudaMemcpyHostToDevice);
-        for (uint64_t base = 0; base < P && e == cudaSuccess; base += CH) {
-            uint64_t n = std::min<uint64_t>(CH, P - base);
-            e = cudaMemcpy(d_cdoc, c->post_doc + base, sizeof(uint32_t) * n, cudaMemcpyHostToDevice);
-            if (e == cudaSuccess) e = cudaMemcpy(d_ctf, c->post_tf + base, sizeof(uint32_t) * n, cudaMemcpyHostToDevice);
-            if (e == cudaSuccess) {
-                k_build_postings<<<(unsigned)((n + 255) / 256), 256>>>(d_cdoc, d_ctf, base, n, d_off, d.post_off, T,
-                                                                       d.fieldnorm, d.post);
-                e = cudaGetLastError();
-            }
-            if (e == cudaSuccess) e = cudaDeviceSynchronize();
-        }
-        if (e == cudaSuccess) e = index_finish_device(ix);
-        cudaFree(d_off);
-        cudaFree(d_cdoc);
-        cudaFree(d_ctf);
-        if (e != cudaSuccess) {
-            bm25x_set_error("bm25x_index_create: posting upload failed: %s", cudaGetErrorString(e));
-            bm25x_index_destroy(ix);
-            return e == cudaErrorMemoryAllocation ? BM25X_ERR_OOM : BM25X_ERR_CUDA;
-        }
-    }
+    rc = upload_csr(ix, "bm25x_index_create", T, P, c->post_off, c->post_doc, c->post_tf);
+    if (rc != BM25X_OK) return rc;
     *out = ix;
     return BM25X_OK;
 }
@@ -582,6 +596,93 @@ extern "C" int bm25x_index_create_from_blocks(const bm25x_blocks *c, int device,
         bm25x_index_destroy(ix);
         return BM25X_ERR_UNSUPPORTED;
     }
+    *out = ix;
+    return BM25X_OK;
+}
+
+// ---- f3: the growing segment (documents inserted since the last seal, search.rs:83-135) as a second, small index that
+// scores with the sealed segment's statistics.  The reference scans these documents one by one per query; here they
+// are inverted once (term-major postings over growing ordinals) so that the same kernels unite them. ----
+extern "C" int bm25x_growing_create(const bm25x_index *sealed, const bm25x_growing_docs *g, bm25x_index **out) {
+    const char *who = "bm25x_growing_create";
+    if (!sealed || !g || !out) {
+        bm25x_set_error("%s: null argument", who);
+        return BM25X_ERR_INVALID;
+    }
+    *out = nullptr;
+    const uint32_t G = g->n_docs, T = sealed->d.n_terms;
+    if (!g->elem_off || (g->elem_off[G] && (!g->elem_term || !g->elem_tf))) {
+        bm25x_set_error("%s: empty or malformed corpus", who);
+        return BM25X_ERR_INVALID;
+    }
+    int rc = check_common(who, G, g->doc_len ? (const void *)g->doc_len : (const void *)g->doc_fieldnorm, sealed->k1,
+                          sealed->b, sealed->device);
+    if (rc != BM25X_OK) return rc;
+    // pass 1: validate the documents (vector.rs:39-75: keys strictly ascending, tf != 0) and count per-term postings
+    std::vector<uint64_t> off((size_t)T + 1, 0);
+    int bad = 0;
+    for (uint32_t d = 0; d < G; d++) {
+        const uint64_t e0 = g->elem_off[d], e1 = g->elem_off[d + 1];
+        if (e1 < e0 || e1 > g->elem_off[G]) {
+            bad |= 1;
+            break;
+        }
+        if (g->deleted && g->deleted[d]) continue;  // VectorTuple.deleted (search.rs:110)
+        bool have_prev = false;
+        uint32_t prev = 0;
+        for (uint64_t e = e0; e < e1; e++) {
+            const uint32_t t = g->elem_term[e], f = g->elem_tf[e];
+            if (f == 0) bad |= 1;
+            if (t == BM25X_TERM_MISSING) continue;  // token unknown to the sealed segment: never matches (search.rs:60-62)
+            if (have_prev && t <= prev) bad |= 1;
+            have_prev = true;
+            prev = t;
+            if (t >= T || sealed->h_df[t] == 0) continue;
+            if (f >= (1u << 24)) bad |= 2;
+            off[(size_t)t + 1]++;
+        }
+    }
+    if (bad & 1) {
+        bm25x_set_error("%s: corrupt documents (term ordinals must be strictly ascending per document, tf != 0)", who);
+        return BM25X_ERR_INVALID;
+    }
+    if (bad & 2) {
+        bm25x_set_error("%s: term frequency >= 2^24 is not supported by the packed posting layout", who);
+        return BM25X_ERR_UNSUPPORTED;
+    }
+    std::vector<uint32_t> df(T);
+    for (uint32_t t = 0; t < T; t++) {
+        df[t] = (uint32_t)off[(size_t)t + 1];
+        off[(size_t)t + 1] += off[t];
+    }
+    const uint64_t P = off[T];
+    // pass 2: invert (documents are visited in ascending ordinal, so every term's list comes out ascending)
+    std::vector<uint32_t> post_doc(P ? P : 1), post_tf(P ? P : 1);
+    {
+        std::vector<uint64_t> cur(off.begin(), off.end() - 1);
+        for (uint32_t d = 0; d < G; d++) {
+            if (g->deleted && g->deleted[d]) continue;
+            for (uint64_t e = g->elem_off[d]; e < g->elem_off[d + 1]; e++) {
+                const uint32_t t = g->elem_term[e];
+                if (t == BM25X_TERM_MISSING || t >= T || sealed->h_df[t] == 0) continue;
+                post_doc[cur[t]] = d;
+                post_tf[cur[t]] = g->elem_tf[e];
+                cur[t]++;
+            }
+        }
+    }
+    BuildMeta m{G, T, g->doc_len, g->payload, sealed->h_keys.empty() ? nullptr : sealed->h_keys.data(), sealed->k1,
+                sealed->b, df.data(), P};
+    m.fieldnorm = g->doc_fieldnorm;
+    m.stat_df = sealed->h_df.data();
+    m.stat_n_docs = sealed->d.n_docs;
+    m.stat_avgdl = sealed->avgdl;
+    bm25x_index *ix = nullptr;
+    rc = index_begin(m, sealed->device, &ix);
+    if (rc != BM25X_OK) return rc;
+    rc = upload_csr(ix, who, T, P, off.data(), post_doc.data(), post_tf.data());
+    if (rc != BM25X_OK) return rc;
+    ix->prune = sealed->prune;
     *out = ix;
     return BM25X_OK;
 }

@@ -411,6 +411,100 @@ extern "C" int bm25x_search_batch(bm25x_index *ix, uint32_t nq, const uint32_t *
     return rc;
 }
 
+// ---- sealed + growing segment (search.rs:83-135 then :137-282 share one Results heap): both top-k lists, merged ----
+extern "C" int bm25x_merge_topk(uint32_t nq, uint32_t k, const uint32_t *doc_a, const float *score_a,
+                                const double *score64_a, const uint16_t *payload_a, const uint32_t *n_a,
+                                const uint32_t *doc_b, const float *score_b, const double *score64_b,
+                                const uint16_t *payload_b, const uint32_t *n_b, uint32_t doc_base_b, uint32_t *out_doc,
+                                float *out_score, double *out_score64, uint16_t *out_payload, uint32_t *out_n) {
+    if (k == 0) {
+        bm25x_set_error("number of needed rows is set to 0");
+        return BM25X_ERR_LIMIT_ZERO;
+    }
+    if (nq && (!doc_a || !score64_a || !n_a || !doc_b || !score64_b || !n_b || !out_doc || !out_n) ||
+        (out_score && (!score_a || !score_b)) || (out_payload && (!payload_a || !payload_b))) {
+        bm25x_set_error("bm25x_merge_topk: null argument (f64 scores of both lists are required)");
+        return BM25X_ERR_INVALID;
+    }
+#pragma omp parallel for schedule(static)
+    for (uint32_t q = 0; q < nq; q++) {
+        const size_t base = (size_t)q * k;
+        const uint32_t na = std::min(n_a[q], k), nb = std::min(n_b[q], k);
+        uint32_t ia = 0, ib = 0, o = 0;
+        while (o < k && (ia < na || ib < nb)) {
+            // score desc; on equal scores list a first: its doc ids are all below doc_base_b (canonical doc-id order)
+            const bool take_a = ib >= nb || (ia < na && score64_a[base + ia] >= score64_b[base + ib]);
+            const size_t src = base + (take_a ? ia : ib);
+            out_doc[base + o] = take_a ? doc_a[src] : doc_b[src] + doc_base_b;
+            if (out_score) out_score[base + o] = take_a ? score_a[src] : score_b[src];
+            if (out_score64) out_score64[base + o] = take_a ? score64_a[src] : score64_b[src];
+            if (out_payload)
+                for (int c = 0; c < 3; c++)
+                    out_payload[(base + o) * 3 + c] = take_a ? payload_a[src * 3 + c] : payload_b[src * 3 + c];
+            take_a ? ia++ : ib++;
+            o++;
+        }
+        out_n[q] = o;
+        for (; o < k; o++) {
+            out_doc[base + o] = BM25X_DOC_INF;
+            if (out_score) out_score[base + o] = 0.f;
+            if (out_score64) out_score64[base + o] = 0.0;
+            if (out_payload) out_payload[(base + o) * 3] = out_payload[(base + o) * 3 + 1] = out_payload[(base + o) * 3 + 2] = 0;
+        }
+    }
+    return BM25X_OK;
+}
+
+extern "C" int bm25x_search_batch_growing(bm25x_index *sealed, bm25x_index *growing, uint32_t nq, const uint32_t *q_off,
+                                          const uint32_t *q_terms, uint32_t k, const uint8_t *allow_sealed,
+                                          const uint8_t *allow_growing, uint32_t *out_doc, float *out_score,
+                                          double *out_score64, uint16_t *out_payload, uint32_t *out_n,
+                                          bm25x_search_stats *stats) {
+    if (!growing)
+        return bm25x_search_batch(sealed, nq, q_off, q_terms, k, allow_sealed, out_doc, out_score, out_score64,
+                                  out_payload, out_n, stats);
+    if (!sealed || sealed->d.n_terms != growing->d.n_terms || sealed->device != growing->device) {
+        bm25x_set_error("bm25x_search_batch_growing: the growing segment does not belong to this sealed index");
+        return BM25X_ERR_INVALID;
+    }
+    if (k == 0) {
+        bm25x_set_error("number of needed rows is set to 0");
+        return BM25X_ERR_LIMIT_ZERO;
+    }
+    const size_t slots = (size_t)nq * k;
+    std::vector<uint32_t> doc[2], n[2];
+    std::vector<float> sc[2];
+    std::vector<double> sc64[2];
+    std::vector<uint16_t> pay[2];
+    bm25x_search_stats st[2];
+    bm25x_index *seg[2] = {sealed, growing};
+    const uint8_t *allow[2] = {allow_sealed, allow_growing};
+    for (int s = 0; s < 2; s++) {
+        doc[s].resize(slots ? slots : 1);
+        n[s].resize(nq ? nq : 1);
+        sc[s].resize(slots ? slots : 1);
+        sc64[s].resize(slots ? slots : 1);
+        if (out_payload) pay[s].resize(slots ? slots * 3 : 1);
+        const int rc = bm25x_search_batch(seg[s], nq, q_off, q_terms, k, allow[s], doc[s].data(), sc[s].data(),
+                                          sc64[s].data(), out_payload ? pay[s].data() : nullptr, n[s].data(), &st[s]);
+        if (rc != BM25X_OK) return rc;
+    }
+    if (stats) {
+        *stats = st[0];
+        stats->kernel_ms += st[1].kernel_ms;
+        stats->h2d_ms += st[1].h2d_ms;
+        stats->d2h_ms += st[1].d2h_ms;
+        stats->postings += st[1].postings;
+        stats->bytes_algo += st[1].bytes_algo;
+        stats->launches += st[1].launches;
+        stats->postings_fetched += st[1].postings_fetched;
+    }
+    return bm25x_merge_topk(nq, k, doc[0].data(), sc[0].data(), sc64[0].data(), out_payload ? pay[0].data() : nullptr,
+                            n[0].data(), doc[1].data(), sc[1].data(), sc64[1].data(),
+                            out_payload ? pay[1].data() : nullptr, n[1].data(), sealed->d.n_docs, out_doc, out_score,
+                            out_score64, out_payload, out_n);
+}
+
 // ---------------------------------------------------------------------------------------------
 uint32_t bm25x_fieldnorm_to_length(uint8_t fn);
 
