@@ -1,10 +1,11 @@
 // bm25x_search_wq.cuh — kernel v5: one WARP per query (sm_100a), for k <= 128 and <= 8 live terms.
 //
 // Every warp of the persistent grid is a complete, independent query engine: it fetches a query from the global work
-// counter, plans its own doc-id chunks (lane j = term j, same block-quota rule as the CTA kernel), streams them into
-// its private double-buffered shared-memory stages with TMA bulk copies (cp.async.bulk + mbarrier), unites the
-// chunk's runs with its private tag map (mark / test / resolve — see bm25x_search_kernel.cuh), re-scores the
-// survivors of the f32 filter exactly in f64 and keeps its own candidate pool.  No CTA barrier, no producer or
+// counter, plans its own doc-id chunks (lane j = term j; every term loads exactly quota*128 postings from where the
+// previous window ended), streams them into its private single-buffered shared-memory stage with TMA bulk copies
+// (cp.async.bulk + mbarrier; the other warps of the SM hide the load latency), unites the chunk's runs with its
+// private tag map(s) (mark / test / resolve), re-scores the survivors of the f32 filter exactly in f64 and keeps its
+// own candidate pool.  No CTA barrier, no producer or
 // splitter warp, no shared pool: nothing a warp does depends on another warp.
 //
 // Exactness is the same argument as the CTA kernel: the f32 filter rejects only F < Sk·(1-2^-18)
