@@ -132,3 +132,27 @@ def test_encode_blocks_matches_corpus():
         if hi > lo:
             assert np.array_equal(np.concatenate(docs), c.post_doc[lo:hi])
             assert np.array_equal(np.concatenate(tfs), c.post_tf[lo:hi])
+
+
+def test_roundtrip_property_based():
+    # hypothesis version of the reference's random round trips: arbitrary lengths, gaps and magnitudes
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.integers(1, 128), st.integers(0, 32), st.integers(0, 2 ** 32 - 1), st.randoms(use_true_random=False))
+    def check(n, bits, start, rnd):
+        hi = (1 << bits) - 1 if bits else 0
+        gaps = [rnd.randint(0, hi) for _ in range(n)]
+        docs, cur = [], start
+        for g in gaps:                      # ascending ids that stay inside u32
+            cur = min(cur + g, 2 ** 32 - 1)
+            docs.append(cur)
+        docs = np.array(docs, dtype=np.uint32)
+        meta, payload = orc.compress_document_ids(int(docs[0]), docs)
+        assert (meta >> 7 == 0) == (n == 128)
+        assert np.array_equal(orc.decompress_document_ids(int(docs[0]), meta, payload), docs)
+        tfs = np.array([rnd.randint(0, hi) for _ in range(n)], dtype=np.uint32)
+        meta, payload = orc.compress_term_frequencies(tfs)
+        assert np.array_equal(orc.decompress_term_frequencies(meta, payload), tfs)
+
+    check()
