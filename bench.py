@@ -92,10 +92,35 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+METRIC = "queries/sec + achieved HBM GB/s, 10M-doc synthetic corpus, top-10"   # BASELINE.json's metric, both arms
+REF_SAMPLE = 20_000   # queries per step of the CPU arms: the FIRST 20k queries of the batch, on every box
+
+
+def effective_cores():
+    """Host threads this process may really use: the affinity mask, capped by the cgroup CPU quota
+    (os.cpu_count() ignores both: round 1 reported 128 "cores" on a box that granted ~12)."""
+    n = len(os.sched_getaffinity(0))
+    quota = None
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            quota = float(q) / float(per)
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / per
+        except Exception:
+            pass
+    eff = n if quota is None else max(1, min(n, int(quota + 0.5)))
+    return eff, {"affinity": n, "cgroup_quota": quota, "os_cpu_count": os.cpu_count()}
+
+
 def measured_traffic(workload, nq, k):
-    """dram__bytes_read.sum + dram__bytes_write.sum of the search kernel from the committed ncu capture of this exact
-    launch (profiles/r1b_traffic.json — newest kernel first), else None."""
-    for name in ("r1b_traffic.json",):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the search kernel from the COMMITTED ncu capture of this exact
+    launch (profiles/*_traffic.json — newest kernel first; not measured in this run), else None."""
+    for name in ("r2_traffic.json",):
         try:
             t = json.load(open(os.path.join(ROOT, "profiles", name)))
             if t["workload"] == workload and t["queries"] == nq and t["k"] == k:
@@ -108,7 +133,10 @@ def measured_traffic(workload, nq, k):
 def kernel_name(tmax, k):
     """The kernel instance the library launches for the widest query class of the workload (bm25x_search.cu)."""
     cls = next(c for c in (1, 2, 3, 4, 8, 16, 32) if c >= tmax)
-    if k <= 128 and cls <= 8:
+    gen = os.environ.get("BM25X_KERNEL", "ring")
+    if gen == "ring":
+        return f"k_search_ring<RCfg<{cls},{64 if k <= 32 else 256 if k <= 224 else 2048}>>"
+    if gen == "wq" and k <= 128 and cls <= 8:
         return f"k_search_wq<WCfg<{cls},{128 if k <= 32 else 256}>>"
     return f"k_search<KCfg<{cls}>>"
 
@@ -121,21 +149,50 @@ def hbm_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def cpu_reference(oracle, oix, q_off, q_terms, k, budget_s, threads):
-    """Times the restated reference algorithm (Block-max WAND, search.rs:28-282) on a bounded sample."""
-    nq = len(q_off) - 1
-    pilot = min(nq, max(threads * 4, 64))
-
-    def run(n):
-        sub_off = (q_off[:n + 1] - q_off[0]).astype(np.uint32)
-        t0 = time.perf_counter()
-        _, _, _, st = oix.search_batch(sub_off, q_terms[q_off[0]:q_off[n]], k, nthreads=threads, wand=True)
-        return time.perf_counter() - t0, st
-
-    dt, _ = run(pilot)
-    n = int(min(nq, max(pilot, pilot * budget_s / max(dt, 1e-6))))
-    dt, st = run(n)
+def cpu_reference(oix, q_off, q_terms, k, n, threads):
+    """Times the restated reference algorithm (Block-max WAND, search.rs:28-282) on the first n queries."""
+    n = min(n, len(q_off) - 1)
+    sub_off = (q_off[:n + 1] - q_off[0]).astype(np.uint32)
+    t0 = time.perf_counter()
+    _, _, _, st = oix.search_batch(sub_off, q_terms[q_off[0]:q_off[n]], k, nthreads=threads, wand=True)
+    dt = time.perf_counter() - t0
     return n / dt, n, dt, st
+
+
+def reference_arm(a, wl, k, cores, cores_how):
+    """`--impl reference`: the reference's own CPU algorithm for this path (oracle/: Block-max WAND restatement, the
+    reference itself is Rust + pgrx and cannot be built here) on the host cores.  Corpus and queries come from the
+    oracle's own generator (bit-identical to the product's, tests/test_abi.py): the product library is never loaded."""
+    from oracle import oracle
+    oracle.build()
+    t0 = time.time()
+    oc = oracle.Corpus.synth_bulk(wl["seed"], wl["docs"], wl["vocab"], wl["doclen"], wl["doclen"], wl["zipf"],
+                                  nthreads=cores)
+    t_gen = time.time() - t0
+    q_off, q_terms = oracle.gen_queries_bulk(wl["seed"] + 1000, wl["queries"], wl["vocab"], wl["tmin"], wl["tmax"],
+                                             oc.post_off, wl["zipf"])
+    nq = wl["queries"]
+    oix = oracle.OracleIndex(oc)
+    n = min(REF_SAMPLE, nq)
+    sub_off, sub_terms = q_off[:n + 1].astype(np.uint32), q_terms[:q_off[n]]
+    for _ in range(max(1, a.warmup)):
+        oix.search_batch(sub_off, sub_terms, k, nthreads=cores, wand=True)
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        oix.search_batch(sub_off, sub_terms, k, nthreads=cores, wand=True)
+    el = time.perf_counter() - t0
+    qps = n * a.steps / el
+    config = {"workload": wl["desc"], "n_docs": wl["docs"], "vocab": wl["vocab"], "doc_len": wl["doclen"],
+              "queries_per_gpu_per_step": nq, "terms_per_query": [wl["tmin"], wl["tmax"]], "k": k,
+              "zipf_s": wl["zipf"], "postings": int(oc.post_off[-1]), "gen_s": round(t_gen, 1)}
+    line = {"impl": "reference", "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": a.gpus,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * el / a.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+            "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "cores_how": cores_how, "kind": "port",
+                             "sample": f"first {n} of the {nq} queries per step, Block-max WAND restatement of "
+                                       f"crates/bm25/src/search.rs (oracle/bm25_oracle.c), one query per OpenMP thread"},
+            "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
 
 
 def main():
@@ -151,20 +208,21 @@ def main():
     if a.k:
         wl["k"] = a.k
     k = wl["k"]
-    cores = os.cpu_count() or 1
+    cores, cores_how = effective_cores()
 
-    if a.impl == "reference" and rank != 0:
-        return  # the reference arm runs on rank 0 only
+    if a.impl == "reference":
+        if rank == 0:
+            reference_arm(a, wl, k, cores, cores_how)
+        return  # the reference arm runs on rank 0 only; it never loads the product library
     import _pkg
     m = _pkg.load()
     m.load_library()
-    use_gpu = a.impl != "reference"
-    if use_gpu:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        if world > 1:
-            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    use_gpu = True
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     # rank 0 generates the corpus and builds the index; the other ranks receive a replica over NCCL (load time only)
     t0 = time.time()
     corpus = None
@@ -202,33 +260,6 @@ def main():
                         "`value` is top-10, the `top100` object is the same batch at k=100",
               "gen_s": round(t_gen, 1), "index_build_s": round(t_index, 1), "replicate_s": round(t_repl, 2)}
 
-    if a.impl == "reference":
-        from oracle import oracle
-        oracle.build()
-        oc = oracle.Corpus(corpus.n_docs, corpus.doc_len, corpus.n_terms, corpus.post_off, corpus.post_doc,
-                           corpus.post_tf)
-        oix = oracle.OracleIndex(oc)
-        per_step_budget = min(a.cpu_seconds, 120.0 / max(1, a.steps + a.warmup))
-        qps0, n, dt, _ = cpu_reference(oracle, oix, q_off, q_terms, k, per_step_budget, cores)
-        sub_off = q_off[:n + 1].astype(np.uint32)
-        for _ in range(max(0, a.warmup - 1)):
-            oix.search_batch(sub_off, q_terms[:q_off[n]], k, nthreads=cores, wand=True)
-        t0 = time.perf_counter()
-        for _ in range(a.steps):
-            oix.search_batch(sub_off, q_terms[:q_off[n]], k, nthreads=cores, wand=True)
-        el = time.perf_counter() - t0
-        qps = n * a.steps / el
-        line = {"impl": "reference", "metric": "queries/sec, 10M-doc synthetic corpus, top-10", "value": qps,
-                "unit": "queries/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
-                "ms_per_step": 1e3 * el / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f64", "data": "synthetic", "config": config,
-                "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
-                                 "sample": f"{n} of the {nq} queries per step, Block-max WAND restatement "
-                                           f"(oracle/bm25_oracle.c), OpenMP over queries"},
-                "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
-        return
-
     info = index.info()
     if a.no_prune:
         index.set_option("prune", 0)
@@ -240,12 +271,12 @@ def main():
         oc = oracle.Corpus(corpus.n_docs, corpus.doc_len, corpus.n_terms, corpus.post_off, corpus.post_doc,
                            corpus.post_tf)
         oix = oracle.OracleIndex(oc)
-        qps, n, dt, st = cpu_reference(oracle, oix, q_off, q_terms, k, a.cpu_seconds, cores)
-        qps1, n1, dt1, _ = cpu_reference(oracle, oix, q_off, q_terms, k, a.cpu_seconds / 3, 1)
-        cpu_baseline = {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
+        qps, n, dt, st = cpu_reference(oix, q_off, q_terms, k, REF_SAMPLE, cores)
+        qps1, n1, dt1, _ = cpu_reference(oix, q_off, q_terms, k, max(200, REF_SAMPLE // 20), 1)
+        cpu_baseline = {"value": qps, "unit": "queries/s", "cores": cores, "cores_how": cores_how, "kind": "port",
                         "sample": f"first {n} of the {nq} queries ({dt:.1f} s), Block-max WAND restatement of "
                                   f"crates/bm25/src/search.rs (oracle/bm25_oracle.c), one query per OpenMP thread",
-                        "single_thread_qps": qps1,
+                        "single_thread_qps": qps1, "single_thread_sample": n1,
                         "wand_postings_touched_frac": st.postings_touched / max(1, sum(
                             int(corpus.post_off[t + 1] - corpus.post_off[t]) for t in q_terms[:q_off[n]]))}
         del oix, oc
@@ -335,8 +366,7 @@ def main():
     achieved = bytes_algo / (kms / 1e3) / 1e9
     h2d = 4 * (len(q_off) + len(q_terms) + nq)       # class-grouped ids + offsets + terms
     d2h = nq * k * 8 + nq * 4
-    line = {"metric": "queries/sec, 10M-doc synthetic corpus, top-10 (+ achieved HBM GB/s in `roofline`)",
-            "value": value, "unit": "queries/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+    line = {"metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 filter + f64 exact re-score (u32 doc ids)", "data": "synthetic", "config": config,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -120,7 +120,8 @@ uint32_t orc_compress_document_ids(uint32_t min_doc, const uint32_t *docs, uint3
     if (by == 0) by = 1; /* bytepacking_u32_ordered.rs:29 div_ceil(8).max(1) */
     uint32_t last = min_doc;
     for (uint32_t i = 0; i < n; i++) { /* bytepacking_u32_ordered.rs:37-60: low `by` bytes, little endian */
-        const uint32_t dl = docs[i] - last;
+        /* byte width 4 stores the ids themselves, no delta (bytepacking_u32_ordered.rs:195: `4 => copy_from_slice`) */
+        const uint32_t dl = by == 4 ? docs[i] : docs[i] - last;
         for (uint8_t k = 0; k < by; k++) out[(size_t)i * by + k] = (uint8_t)(dl >> (8 * k));
         last = docs[i];
     }
@@ -151,7 +152,8 @@ uint32_t orc_decompress_document_ids(uint32_t min_doc, uint8_t meta, const uint8
     for (uint32_t i = 0; i < n; i++) {
         uint32_t dl = 0;
         for (uint8_t k = 0; k < width; k++) dl |= (uint32_t)in[(size_t)i * width + k] << (8 * k);
-        state += dl;
+        /* width 4: raw ids, the running sum is not applied (bytepacking_u32_ordered.rs:211) */
+        state = width == 4 ? dl : state + dl;
         docs[i] = state;
     }
     return n;

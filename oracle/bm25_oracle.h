@@ -120,6 +120,13 @@ int orc_synth_doc(uint64_t seed, uint32_t doc, uint32_t vocab, uint32_t len_min,
                   uint32_t len_max, const uint64_t *zipf_thr, uint32_t *terms_out,
                   uint32_t *tfs_out, uint32_t *len_out);
 
+/* Bulk forms (bm25_synth.c): the whole corpus as term-major CSR, and a batch of queries. */
+int orc_synth_corpus(uint64_t seed, uint32_t n_docs, uint32_t vocab, uint32_t len_min, uint32_t len_max, double zipf_s,
+                     int nthreads, uint32_t *doc_len, uint64_t *post_off, uint32_t *post_doc, uint32_t *post_tf,
+                     uint64_t cap, uint64_t *n_post_out);
+int orc_synth_queries(uint64_t seed, uint32_t nq, uint32_t vocab, uint32_t nmin, uint32_t nmax, double zipf_s,
+                      const uint64_t *post_off, uint32_t *q_off, uint32_t *q_terms);
+
 /* ---- posting-block codec (bm25_codec.c): compression.rs:36-136 + crates/simd bit/byte packing ---- */
 uint32_t orc_compress_document_ids(uint32_t min_doc, const uint32_t *docs, uint32_t n, uint8_t *meta, uint8_t *out);
 uint32_t orc_decompress_document_ids(uint32_t min_doc, uint8_t meta, const uint8_t *in, uint32_t n_bytes,

@@ -18,7 +18,7 @@ _SO = os.path.join(_HERE, "libbm25_oracle.so")
 
 def build(force: bool = False) -> str:
     """Compile the oracle with the committed Makefile (gcc, seconds)."""
-    srcs = [os.path.join(_HERE, f) for f in ("bm25_oracle.c", "bm25_codec.c", "bm25_oracle.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("bm25_oracle.c", "bm25_codec.c", "bm25_synth.c", "bm25_oracle.h")]
     if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return _SO
@@ -88,6 +88,12 @@ def lib():
     L.orc_draw.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32]
     L.orc_draw_term.restype = C.c_uint32
     L.orc_draw_term.argtypes = [C.c_uint64, C.c_uint32, u64p]
+    L.orc_synth_corpus.restype = C.c_int
+    L.orc_synth_corpus.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_double, C.c_int, u32p,
+                                   u64p, u32p, u32p, C.c_uint64, u64p]
+    L.orc_synth_queries.restype = C.c_int
+    L.orc_synth_queries.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_double, u64p, u32p,
+                                    u32p]
     L.orc_synth_doc.restype = C.c_int
     L.orc_synth_doc.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, u64p, u32p, u32p, u32p]
     L.orc_search_growing.restype = C.c_int
@@ -151,6 +157,24 @@ class Corpus:
                 pt.append(tf)
         return Corpus(n_docs, doc_len, n_terms, off, np.array(pd, dtype=np.uint32), np.array(pt, dtype=np.uint32),
                       k1, b)
+
+    @staticmethod
+    def synth_bulk(seed, n_docs, vocab, len_min, len_max=None, zipf_s=0.0, nthreads=0, k1=1.2, b=0.75):
+        """The same corpus as synth(), generated in C for full-size configs (bm25_synth.c, OpenMP)."""
+        L = lib()
+        len_max = len_min if len_max is None else len_max
+        nthreads = nthreads or len(os.sched_getaffinity(0))
+        cap = int(n_docs) * int(max(len_max, 1))
+        doc_len = np.zeros(n_docs, dtype=np.uint32)
+        off = np.zeros(vocab + 1, dtype=np.uint64)
+        pd = np.empty(max(cap, 1), dtype=np.uint32)
+        pt = np.empty(max(cap, 1), dtype=np.uint32)
+        n = C.c_uint64(0)
+        rc = L.orc_synth_corpus(seed, n_docs, vocab, len_min, len_max, zipf_s, nthreads, _p(doc_len, C.c_uint32),
+                                _p(off, C.c_uint64), _p(pd, C.c_uint32), _p(pt, C.c_uint32), cap, C.byref(n))
+        if rc != 0:
+            raise RuntimeError(f"orc_synth_corpus failed ({rc})")
+        return Corpus(n_docs, doc_len, vocab, off, pd[:n.value], pt[:n.value], k1, b)
 
     @staticmethod
     def synth(seed, n_docs, vocab, len_min, len_max=None, zipf_s=0.0, k1=1.2, b=0.75):
@@ -287,6 +311,18 @@ def gen_queries(seed, nq, vocab, nterms_min, nterms_max, df_of, zipf_s=0.0):
         out.extend(got)
         off.append(len(out))
     return np.array(off, dtype=np.uint32), np.array(out, dtype=np.uint32)
+
+
+def gen_queries_bulk(seed, nq, vocab, nterms_min, nterms_max, post_off, zipf_s=0.0):
+    """gen_queries() in C (bm25_synth.c) for full-size batches."""
+    q_off = np.zeros(nq + 1, dtype=np.uint32)
+    q_terms = np.zeros(max(nq * nterms_max, 1), dtype=np.uint32)
+    post_off = np.ascontiguousarray(post_off, dtype=np.uint64)
+    rc = lib().orc_synth_queries(seed, nq, vocab, nterms_min, nterms_max, zipf_s, _p(post_off, C.c_uint64),
+                                 _p(q_off, C.c_uint32), _p(q_terms, C.c_uint32))
+    if rc != 0:
+        raise RuntimeError(f"orc_synth_queries failed ({rc})")
+    return q_off, q_terms[:int(q_off[-1])].copy()
 
 
 # ---- posting-block codec (bm25_codec.c; compression.rs:36-136) ----

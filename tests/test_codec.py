@@ -156,3 +156,23 @@ def test_roundtrip_property_based():
         assert np.array_equal(orc.decompress_term_frequencies(meta, payload), tfs)
 
     check()
+
+
+def test_layout_bytewidth4_is_raw_not_delta():
+    """A token's last block whose largest gap needs 4 bytes stores the ids THEMSELVES, little endian, no delta
+    (crates/simd/src/bytepacking_u32_ordered.rs:195 `4 => output.copy_from_slice(as_bytes(input))`, :211 the raw copy
+    back; widths 1..3 store deltas, :37-60).  Byte string derived by hand from those two lines."""
+    docs = np.array([7, 7 + (1 << 24) + 5, 0x03020100, 0xFFFFFFF0], dtype=np.uint32)
+    meta, payload = orc.compress_document_ids(7, docs)
+    assert meta == (0x80 | 4) and len(payload) == 16
+    want = bytes([7, 0, 0, 0,   12, 0, 0, 1,   0x00, 0x01, 0x02, 0x03,   0xF0, 0xFF, 0xFF, 0xFF])
+    assert payload.tobytes() == want
+    assert np.array_equal(orc.decompress_document_ids(7, meta, payload), docs)
+    # `min` is ignored by the raw form: any seed decodes to the same ids
+    assert np.array_equal(orc.decompress_document_ids(123456, meta, payload), docs)
+    # one byte narrower: deltas against the previous id, the first against min
+    docs3 = np.array([7, 7 + (1 << 24) - 1, 7 + (1 << 24) + 2], dtype=np.uint32)
+    meta, payload = orc.compress_document_ids(7, docs3)
+    assert meta == (0x80 | 3)
+    assert payload.tobytes() == bytes([0, 0, 0,   0xFF, 0xFF, 0xFF,   3, 0, 0])
+    assert np.array_equal(orc.decompress_document_ids(7, meta, payload), docs3)

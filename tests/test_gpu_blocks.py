@@ -114,6 +114,35 @@ def test_blocks_wide_deltas_and_tf_limits(m, orc):
         build(tfs)
 
 
+def test_blocks_bytewidth4_tail_is_raw(m, orc):
+    """A 77-posting tail block with a gap >= 2^24 is byte-packed with width 4 = raw ids, no delta
+    (crates/simd/src/bytepacking_u32_ordered.rs:195,211); routine for rare terms of a 50M-document index."""
+    N = 60_000_000
+    rng = np.random.default_rng(9)
+    head = np.sort(rng.choice(1_000_000, 128, replace=False)).astype(np.uint32)
+    first = np.uint32(1_000_007)
+    second = np.uint32(int(first) + (1 << 24) + 5)
+    rest = np.sort(rng.choice(np.arange(int(second) + 1, N), 75, replace=False)).astype(np.uint32)
+    docs = np.concatenate([head, [first, second], rest]).astype(np.uint32)
+    tfs = rng.integers(1, 9, len(docs)).astype(np.uint32)
+    md0, pd0 = orc.compress_document_ids(int(docs[0]), docs[:128])
+    mt0, pt0 = orc.compress_term_frequencies(tfs[:128])
+    md1, pd1 = orc.compress_document_ids(int(docs[128]), docs[128:])
+    mt1, pt1 = orc.compress_term_frequencies(tfs[128:])
+    assert md1 == (0x80 | 4) and len(pd1) == 77 * 4
+    assert pd1.view("<u4").tolist() == docs[128:].tolist()          # the payload IS the id list
+    data = np.concatenate([pd0, pt0, pd1, pt1])
+    offs = np.cumsum([0, len(pd0), len(pt0), len(pd1)])
+    ix = m.Index.from_blocks(N, 1, [0, 2], [docs[0], docs[128]], [128, 77], [md0, md1], [mt0, mt1],
+                             [offs[0], offs[2]], [offs[1], offs[3]], data,
+                             doc_fieldnorm=np.full(N, 20, dtype=np.uint8), sum_doc_len=20 * N)
+    got_d, got_s = ix.search([0], 1000)
+    assert sorted(got_d.tolist()) == docs.tolist()
+    order = np.lexsort((docs, -tfs.astype(np.int64)))               # equal norms: tf desc, then doc id asc
+    assert got_d.tolist() == docs[order].tolist()
+    ix.close()
+
+
 def test_blocks_corruption_is_reported(m, orc):
     c = m.synth_corpus(43, 2000, 20, 8, 40, 0.5)
     eb = orc.EncodedBlocks(orc.Corpus(c.n_docs, c.doc_len, c.n_terms, c.post_off, c.post_doc, c.post_tf))

@@ -48,6 +48,9 @@ __device__ __forceinline__ void decode_stream(const uint8_t *sm, uint8_t meta, u
             unpack4(sm, width, lane, v);
         }
     } else {
+        // a token's last block: 1..4 little-endian bytes per value; width 4 = the values themselves, even for doc ids
+        // (crates/simd/src/bytepacking_u32_ordered.rs:195,211: `4 => copy_from_slice`, no delta)
+        if (width == 4) raw = true;
 #pragma unroll
         for (uint32_t l = 0; l < 4; l++) {
             const uint32_t i = 4u * lane + l;

@@ -57,6 +57,7 @@ struct bm25x_index {
     int sm_count = 0;
     DeviceIndex d;
     double k1 = 1.2, b = 0.75, avgdl = 0;
+    float s1f_min = 0.f;               // min over the documents of s1f[fieldnorm]: one-compare single-term test (k_search_ring)
     uint64_t sum_len = 0;
     uint64_t device_bytes = 0;
     std::vector<uint32_t> h_df;        // host copy for query canonicalisation

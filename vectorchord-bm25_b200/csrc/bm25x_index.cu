@@ -296,6 +296,14 @@ static int index_begin(const BuildMeta &m, int device, bm25x_index **ixp) {
         h_s1d[f] = m.k1 * (1.0 - m.b + m.b * dl / ix->avgdl);
         h_s1f[f] = (float)h_s1d[f];
     }
+    {   // smallest s1 over the documents present: the one-compare single-term test of k_search_ring needs a lower bound
+        bool seen[256] = {false};
+        for (uint32_t d = 0; d < N; d++) seen[h_fn[d]] = true;
+        float mn = 3.0e38f;
+        for (int f = 0; f < 256; f++)
+            if (seen[f] && h_s1f[f] < mn) mn = h_s1f[f];
+        ix->s1f_min = mn;
+    }
     if (m.term_key) ix->h_keys.assign(m.term_key, m.term_key + (size_t)T * 16);
 
     DeviceIndex &d = ix->d;
@@ -768,6 +776,12 @@ extern "C" int bm25x_index_alloc_replica(const bm25x_index_layout *like, int dev
     CU(cudaSetDevice(device));
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        bm25x_set_error("bm25x_index_alloc_replica: device %d is sm_%d%d; this library only carries sm_100a kernels", device,
+                        prop.major, prop.minor);
+        bm25x_index_destroy(ix);
+        return BM25X_ERR_CUDA;
+    }
     ix->sm_count = prop.multiProcessorCount;
     CU(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
     {
@@ -809,6 +823,18 @@ extern "C" int bm25x_index_finalize_replica(bm25x_index *ix) {
     ix->h_df.resize(ix->d.n_terms);
     if (ix->d.n_terms)
         BM25X_CUDA_TRY(cudaMemcpy(ix->h_df.data(), ix->d.df, sizeof(uint32_t) * ix->d.n_terms, cudaMemcpyDeviceToHost));
+    {   // s1f_min from the replicated arrays (see index_begin)
+        std::vector<uint8_t> h_fn(ix->d.n_docs);
+        float h_s1f[256];
+        BM25X_CUDA_TRY(cudaMemcpy(h_fn.data(), ix->d.fieldnorm, ix->d.n_docs, cudaMemcpyDeviceToHost));
+        BM25X_CUDA_TRY(cudaMemcpy(h_s1f, ix->d.s1f, sizeof(h_s1f), cudaMemcpyDeviceToHost));
+        bool seen[256] = {false};
+        for (uint32_t d = 0; d < ix->d.n_docs; d++) seen[h_fn[d]] = true;
+        float mn = 3.0e38f;
+        for (int f = 0; f < 256; f++)
+            if (seen[f] && h_s1f[f] < mn) mn = h_s1f[f];
+        ix->s1f_min = mn;
+    }
     return BM25X_OK;
 }
 

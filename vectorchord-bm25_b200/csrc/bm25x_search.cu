@@ -127,6 +127,17 @@ static int launch_class(const bm25x_index *ix, SearchParams &sp, cudaStream_t st
     return BM25X_OK;
 }
 
+// kernel v6 (bm25x_search_ring.cu: warp per query, ring stages + presence map), one entry per pool capacity
+int bm25x_launch_ring_kp64(int device, int sm_count, const SearchParams &sp, int M, cudaStream_t stream);
+int bm25x_launch_ring_kp256(int device, int sm_count, const SearchParams &sp, int M, cudaStream_t stream);
+int bm25x_launch_ring_kp2048(int device, int sm_count, const SearchParams &sp, int M, cudaStream_t stream);
+
+static int launch_ring_k(const bm25x_index *ix, const SearchParams &sp, int M, cudaStream_t stream) {
+    if (sp.k <= 32) return bm25x_launch_ring_kp64(ix->device, ix->sm_count, sp, M, stream);
+    if (sp.k <= 224) return bm25x_launch_ring_kp256(ix->device, ix->sm_count, sp, M, stream);
+    return bm25x_launch_ring_kp2048(ix->device, ix->sm_count, sp, M, stream);
+}
+
 // kernel v5 (warp per query): k <= 128 and <= 8 live terms
 template <class C>
 static int launch_wq(const bm25x_index *ix, SearchParams &sp, cudaStream_t stream) {
@@ -150,14 +161,16 @@ static int launch_wq_k(const bm25x_index *ix, SearchParams &sp, cudaStream_t str
     return launch_wq<WCfg<M, 256>>(ix, sp, stream);
 }
 
-static bool use_warp_kernel(uint32_t k, int M) {
-    static int forced = -1;  // BM25X_KERNEL=cta forces the CTA-per-query kernel (v4) everywhere
-    if (forced < 0) {
+// BM25X_KERNEL=cta | wq selects the previous kernel generations (A/B timing, tools/time_variants.py); default: ring
+static int kernel_generation() {
+    static int gen = -1;
+    if (gen < 0) {
         const char *e = getenv("BM25X_KERNEL");
-        forced = (e && strcmp(e, "cta") == 0) ? 1 : 0;
+        gen = (e && strcmp(e, "cta") == 0) ? 4 : (e && strcmp(e, "wq") == 0) ? 5 : 6;
     }
-    return !forced && k <= 128 && M <= 8;
+    return gen;
 }
+static bool use_warp_kernel(uint32_t k, int M) { return kernel_generation() == 5 && k <= 128 && M <= 8; }
 
 template <typename T>
 static int batch_alloc(bm25x_batch *b, T **p, size_t n) {
@@ -193,6 +206,10 @@ extern "C" int bm25x_batch_prepare(bm25x_index *ix, uint32_t nq, const uint32_t 
         return BM25X_ERR_INVALID;
     }
     *out = nullptr;
+    if (ix->h_df.size() != ix->d.n_terms) {
+        bm25x_set_error("bm25x_batch_prepare: replica not finalized (bm25x_index_finalize_replica)");
+        return BM25X_ERR_INVALID;
+    }
     if (k == 0) {
         bm25x_set_error("number of needed rows is set to 0");  // scanners/default.rs:114-116
         return BM25X_ERR_LIMIT_ZERO;
@@ -323,6 +340,7 @@ extern "C" int bm25x_batch_run(bm25x_batch *b, void *stream_v, bm25x_search_stat
         sp.payload = d.payload;
         sp.ubd = d.ubd;
         sp.prune = ix->prune;
+        sp.s1f_min = ix->s1f_min;
         sp.fetched = b->d_fetched;
         sp.n_docs = d.n_docs;
         sp.q_ids = g.d_ids;
@@ -339,7 +357,9 @@ extern "C" int bm25x_batch_run(bm25x_batch *b, void *stream_v, bm25x_search_stat
         sp.out_n = b->d_out_n;
         BM25X_CUDA_TRY(cudaMemsetAsync(g.d_counter, 0, sizeof(int), st));
         int rc = BM25X_OK;
-        if (use_warp_kernel(b->k, g.M)) {
+        if (kernel_generation() == 6) {
+            rc = launch_ring_k(ix, sp, g.M, st);
+        } else if (use_warp_kernel(b->k, g.M)) {
             switch (g.M) {
                 case 1: rc = launch_wq_k<1>(ix, sp, st); break;
                 case 2: rc = launch_wq_k<2>(ix, sp, st); break;
@@ -515,6 +535,10 @@ extern "C" int bm25x_evaluate_batch(bm25x_index *ix, uint32_t n_pairs, const uin
         return BM25X_ERR_INVALID;
     }
     if (n_pairs == 0) return BM25X_OK;
+    if (ix->h_df.size() != ix->d.n_terms) {
+        bm25x_set_error("bm25x_evaluate_batch: replica not finalized (bm25x_index_finalize_replica)");
+        return BM25X_ERR_INVALID;
+    }
     BM25X_CUDA_TRY(cudaSetDevice(ix->device));
     const uint32_t nd = d_off[n_pairs], nqt = q_off[n_pairs];
     const uint32_t T = ix->d.n_terms;

@@ -27,6 +27,38 @@
 
 #include "bm25x_common.h"
 
+// One launch = the queries of one term-count class (shared by the translation units of the library).
+struct SearchParams {
+    const Posting *post;
+    const uint64_t *post_off;
+    const uint32_t *df;
+    const uint64_t *blk_off;
+    const uint2 *blk;
+    const float *s0f;
+    const double *s0d;
+    const double *s1d;
+    const float *s1f;
+    const uint16_t *payload;
+    const double *ubd;                  // per-term upper bound of one posting's exact score
+    unsigned long long *fetched;        // Σ postings actually loaded into shared memory (pruning statistics)
+    int prune;
+    float s1f_min;                      // min over the documents of s1f[fieldnorm]
+    uint32_t n_docs;
+    // one launch = the queries of one term-count class
+    const uint32_t *q_ids;    // original query index
+    const uint32_t *q_off;    // [nq+1]
+    const uint32_t *q_terms;  // canonical: ascending, distinct, df > 0
+    uint32_t nq;
+    uint32_t k;
+    const uint8_t *allow;
+    int *work_counter;
+    uint32_t *out_doc;
+    float *out_score;
+    double *out_score64;
+    uint16_t *out_payload;
+    uint32_t *out_n;
+};
+
 namespace {
 
 constexpr uint32_t INF = BM25X_DOC_INF;
@@ -72,36 +104,6 @@ __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src
                  : "memory");
 }
 
-// ---------------------------------------------------------------------------------------------
-struct SearchParams {
-    const Posting *post;
-    const uint64_t *post_off;
-    const uint32_t *df;
-    const uint64_t *blk_off;
-    const uint2 *blk;
-    const float *s0f;
-    const double *s0d;
-    const double *s1d;
-    const float *s1f;
-    const uint16_t *payload;
-    const double *ubd;                  // per-term upper bound of one posting's exact score
-    unsigned long long *fetched;        // Σ postings actually loaded into shared memory (pruning statistics)
-    int prune;
-    uint32_t n_docs;
-    // one launch = the queries of one term-count class
-    const uint32_t *q_ids;    // original query index
-    const uint32_t *q_off;    // [nq+1]
-    const uint32_t *q_terms;  // canonical: ascending, distinct, df > 0
-    uint32_t nq;
-    uint32_t k;
-    const uint8_t *allow;
-    int *work_counter;
-    uint32_t *out_doc;
-    float *out_score;
-    double *out_score64;
-    uint16_t *out_payload;
-    uint32_t *out_n;
-};
 
 template <int M_>
 struct KCfg {

@@ -1,0 +1,45 @@
+// bm25x_search_ring.cu — instantiations of k_search_ring (bm25x_search_ring.cuh) for one pool size.
+// Compiled once per pool capacity (-DBM25X_RING_KP=64|256|2048) so that the term-count classes build in parallel.
+#include "bm25x_common.h"
+
+#include "bm25x_search_ring.cuh"
+
+#ifndef BM25X_RING_KP
+#error "compile with -DBM25X_RING_KP=<pool capacity>"
+#endif
+
+namespace {
+
+template <class C>
+int launch_ring(int device, int sm_count, const SearchParams &sp, cudaStream_t stream) {
+    static bool configured[64] = {false};
+    auto kern = k_search_ring<C>;
+    if (!configured[device & 63]) {
+        BM25X_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::total));
+        configured[device & 63] = true;
+    }
+    uint32_t grid = (uint32_t)sm_count;  // persistent: one CTA per SM, every warp pulls queries from the work counter
+    const uint32_t need = (sp.nq + C::WARPS - 1) / C::WARPS;
+    if (grid > need) grid = need;
+    kern<<<grid, C::THREADS, C::total, stream>>>(sp);
+    BM25X_CUDA_TRY(cudaGetLastError());
+    return BM25X_OK;
+}
+
+}  // namespace
+
+#define BM25X_RING_ENTRY2(kp) bm25x_launch_ring_kp##kp
+#define BM25X_RING_ENTRY(kp) BM25X_RING_ENTRY2(kp)
+
+// M = term-count class of the launch (1, 2, 3, 4, 8, 16, 32)
+int BM25X_RING_ENTRY(BM25X_RING_KP)(int device, int sm_count, const SearchParams &sp, int M, cudaStream_t stream) {
+    switch (M) {
+        case 1: return launch_ring<RCfg<1, BM25X_RING_KP>>(device, sm_count, sp, stream);
+        case 2: return launch_ring<RCfg<2, BM25X_RING_KP>>(device, sm_count, sp, stream);
+        case 3: return launch_ring<RCfg<3, BM25X_RING_KP>>(device, sm_count, sp, stream);
+        case 4: return launch_ring<RCfg<4, BM25X_RING_KP>>(device, sm_count, sp, stream);
+        case 8: return launch_ring<RCfg<8, BM25X_RING_KP>>(device, sm_count, sp, stream);
+        case 16: return launch_ring<RCfg<16, BM25X_RING_KP>>(device, sm_count, sp, stream);
+        default: return launch_ring<RCfg<32, BM25X_RING_KP>>(device, sm_count, sp, stream);
+    }
+}

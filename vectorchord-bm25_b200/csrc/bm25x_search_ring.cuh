@@ -1,0 +1,568 @@
+// bm25x_search_ring.cuh — kernel v6 (sm_100a): one WARP per query, ring stages + presence map.
+//
+// Replaces the per-query cursor walk of bm25::search (crates/bm25/src/search.rs:137-282) for a whole batch: every
+// warp of the persistent grid is a complete query engine (lane j owns term j of its query).
+//
+//   rings     each term ("run") owns a ring of R postings in shared memory, filled by TMA bulk copies
+//             (cp.async.bulk + mbarrier).  A refill appends exactly as many postings as earlier chunks consumed, so
+//             every posting crosses L2 → shared memory once (the v5 kernel re-fetched the unconsumed tail of every
+//             chunk: 1.66 postings loaded per posting consumed).  One refill round is in flight while the previous
+//             one is processed.
+//   window    chunk = doc window [lo, hi): hi = the smallest "last landed doc" over the runs that still have postings
+//             in HBM; each lane binary-searches hi in its run → exact in-window range [rd, e), nothing scanned twice.
+//   union     runs are processed in ascending order; run j first TESTS each of its documents against a byte map that
+//             holds the marks of runs < j, then MARKS it (one multiplicative hash, plain st.shared.u8 of the chunk's
+//             generation tag: idempotent stores, no atomics, no clearing — stale tags of older chunks never match).
+//             A document held by two runs is therefore always detected by the later run's posting (no false
+//             negatives); false alarms (slot shared with another document) are a few per cent.
+//   single    a document held by one run only can enter the top-k only if its term frequency passes the threshold:
+//             one integer compare per posting (w > wlim_j, wlim_j from the exact threshold solved for tf), plus the
+//             tie shortcut (same (run, tf, fieldnorm) signature as the k-th entry ⇒ identical score ⇒ rejected
+//             unless the doc id is smaller).
+//   verify    detected postings are listed (ballot-compacted) and verified 32 at a time: binary search of the
+//             document in the other runs' window ranges, f32 filter score over all holders; the LAST run holding a
+//             document emits it (exactly once per document); survivors of the filter are re-scored in f64 in the
+//             reference's operation order (Cache::evaluate, bm25.rs:355-358, summed over ascending terms) and enter
+//             the warp's pool.
+//   dense     windows in which the runs overlap heavily (head terms) are summed in a dense f32 accumulator indexed by
+//             doc - lo instead (the window is clamped to the accumulator size: a ring can be consumed partially).
+//   pruning   MaxScore-style, as v5 (token-level bounds; non-streamed terms are probed in HBM for candidates).
+//
+// Exactness: the f32 filter only rejects F < Sk·(1-2^-18) and exact-score ties by signature;
+// everything else is ranked by (f64 score desc, doc id asc).
+#pragma once
+
+#include "bm25x_search_wq.cuh"
+
+namespace {
+
+#ifndef BM25X_RING_LOG_R
+#define BM25X_RING_LOG_R -1
+#endif
+#ifndef BM25X_RING_LOG_S
+#define BM25X_RING_LOG_S 13
+#endif
+#ifndef BM25X_RING_U
+#define BM25X_RING_U 2
+#endif
+#ifndef BM25X_RING_MAXWARPS
+#define BM25X_RING_MAXWARPS 16
+#endif
+#ifndef BM25X_RING_INIT
+#define BM25X_RING_INIT 32
+#endif
+#ifndef BM25X_RING_DENSE_T
+#define BM25X_RING_DENSE_T 48
+#endif
+
+template <int M_, int KP_>
+struct RCfg {
+    static constexpr int M = M_;    // max live terms (lanes 0..M-1 own the terms)
+    static constexpr int KP = KP_;  // pool capacity (power of two >= k + 32)
+    // ring postings per run: half a ring is in flight while the other half is processed
+    static constexpr int LOG_R = BM25X_RING_LOG_R > 0 ? BM25X_RING_LOG_R : (M_ <= 4 ? 9 : (M_ <= 8 ? 8 : 7));
+    static constexpr int R = 1 << LOG_R;
+    static constexpr uint32_t RM = R - 1;
+    static constexpr int LOG_S = M_ == 1 ? 8 : BM25X_RING_LOG_S;  // presence map bytes = dense accumulator bytes (unused for one term)
+    static constexpr uint32_t ACC_DOCS = (1u << LOG_S) / 4u;
+    static constexpr int U = BM25X_RING_U;          // 16-byte shared loads (2 postings) per lane and trip
+    static constexpr int TRIP = 64 * U;             // postings per warp trip
+    static constexpr int LCAP = TRIP + 64;          // candidate list entries (verified when > 64 are listed)
+    static constexpr int INIT = BM25X_RING_INIT;    // postings per run in the very first load (a threshold exists early)
+    static constexpr size_t off_ring = 0;
+    static constexpr size_t off_map = off_ring + (size_t)M_ * R * sizeof(Posting);
+    static constexpr size_t off_pool_s = off_map + ((size_t)1 << LOG_S);
+    static constexpr size_t off_pool_d = off_pool_s + (size_t)KP * 8;
+    static constexpr size_t off_pool_g = off_pool_d + (size_t)KP * 4;
+    static constexpr size_t off_cand = off_pool_g + (size_t)KP * 4;
+    static constexpr size_t off_bar = off_cand + (size_t)LCAP * 4;
+    static constexpr size_t warp_bytes = (off_bar + 8 + 127) & ~(size_t)127;
+    static constexpr size_t off_s1f = 0;  // CTA-shared: 1 KiB table first, then the warps
+    static constexpr size_t shared_bytes = 1024;
+    static constexpr int WARPS_FIT = (int)((227 * 1024 - shared_bytes) / warp_bytes);
+    static constexpr int WARPS = WARPS_FIT > BM25X_RING_MAXWARPS ? BM25X_RING_MAXWARPS : WARPS_FIT;
+    static constexpr size_t total = shared_bytes + warp_bytes * WARPS;
+    static constexpr int THREADS = WARPS * 32;
+    static_assert(WARPS >= 1, "one warp must fit");
+    static_assert(R <= 65536 && M_ <= 32, "entry format: 16-bit ring position, 5-bit run");
+    static_assert(ACC_DOCS >= 64, "accumulator too small");
+};
+
+__device__ __forceinline__ uint32_t ring_slot(uint32_t doc, int log_s) { return (doc * 0x9E3779B1u) >> (32 - log_s); }
+
+// lower_bound of `doc` in ring positions [a, e) (posting indices of the term; the ring holds index i at i & RM)
+template <class C>
+__device__ __forceinline__ uint32_t ring_lower_bound(const Posting *rg, uint32_t a, uint32_t e, uint32_t doc) {
+    uint32_t l = a, r = e;
+    while (l < r) {
+        const uint32_t mid = (l + r) >> 1;
+        if (rg[mid & C::RM].doc < doc) l = mid + 1;
+        else r = mid;
+    }
+    return l;
+}
+// posting word of `doc` in [a, e), 0 when absent
+template <class C>
+__device__ __forceinline__ uint32_t ring_find(const Posting *rg, uint32_t a, uint32_t e, uint32_t doc) {
+    const uint32_t l = ring_lower_bound<C>(rg, a, e, doc);
+    if (l < e) {
+        const Posting v = rg[l & C::RM];
+        if (v.doc == doc) return v.w;
+    }
+    return 0u;
+}
+
+template <class C>
+__global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_constant__ SearchParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    constexpr uint32_t FULL = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    float *s1f = (float *)(smem + C::off_s1f);
+    for (int i = threadIdx.x; i < 256; i += C::THREADS) s1f[i] = p.s1f[i];
+    uint8_t *ws = smem + C::shared_bytes + C::warp_bytes * wid;
+    Posting *rings = (Posting *)(ws + C::off_ring);
+    uint8_t *map = ws + C::off_map;
+    WPool<C> pl;
+    pl.s = (uint64_t *)(ws + C::off_pool_s);
+    pl.d = (uint32_t *)(ws + C::off_pool_d);
+    pl.g = (uint32_t *)(ws + C::off_pool_g);
+    uint32_t *cand = (uint32_t *)(ws + C::off_cand);
+    uint64_t *bar = (uint64_t *)(ws + C::off_bar);
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+    }
+    if (C::M > 1)
+        for (int i = lane; i < (1 << C::LOG_S) / 16; i += 32) ((uint4 *)map)[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    const uint32_t k = p.k;
+    const double kEps = 1.0 / 262144.0;
+    const float s1min = p.s1f_min;
+    uint32_t parity = 0;  // mbarrier phase parity
+    uint32_t gen = 0;     // generation tag of the chunk (1..255), never reset: stale tags cost false alarms only
+    Posting *const myring = rings + (size_t)(lane < C::M ? lane : 0) * C::R;
+
+    for (;;) {
+        int qi = 0;
+        if (lane == 0) qi = atomicAdd(p.work_counter, 1);
+        qi = __shfl_sync(FULL, qi, 0);
+        if (qi >= (int)p.nq) break;
+        const uint32_t qid = p.q_ids[qi];
+        const uint32_t t0 = p.q_off[qi];
+        const uint32_t m = p.q_off[qi + 1] - t0;
+        // ---- query terms: lane j < m (TokenTuple of term j: df, postings, score constants) ----
+        uint32_t dfj = 0, dfpad = 0, nbj = 0;
+        uint64_t pbase = 0, bbase = 0;
+        float s0f = 0.f;
+        double s0d = 0.0, ubd = 0.0;
+        if (lane < (int)m) {
+            const uint32_t term = p.q_terms[t0 + lane];
+            dfj = p.df[term];
+            dfpad = (dfj + 1u) & ~1u;
+            pbase = p.post_off[term];
+            bbase = p.blk_off[term];
+            nbj = (dfj + BM25X_BLOCK - 1) / BM25X_BLOCK;
+            s0f = p.s0f[term];
+            s0d = p.s0d[term];
+            ubd = p.ubd[term];
+        }
+        uint32_t rd = 0, wr = 0;  // my run: postings [0, rd) consumed, [rd, wr) in the ring (wr: landed at the next wait)
+        uint32_t lo = 0;          // every posting with doc < lo has been consumed
+        // MaxScore pruning (warp-uniform): terms in ne_mask are no longer streamed; ub_ne = Σ of their score bounds
+        uint32_t ne_mask = 0u;
+        double ub_ne = 0.0;
+        bool thr_new = false;     // the threshold moved since the pruned set was last reconsidered
+        unsigned long long fetched = 0;
+        // per-query pool / threshold state (warp-uniform registers)
+        int pn = 0;
+        WFilter f;
+        f.tv = false;
+        f.Flo = -1.f;
+        f.Sk = 0.0;
+        f.dk = INF;
+        f.tie_sig = SIG_NONE;
+        f.tie_dk = INF;
+        f.ctf = 0.f;
+        uint32_t wlim = 255u;         // lane j: single-term postings of run j can pass only if w > wlim  (tf >= 1: all)
+        uint32_t tiew = 0xFFFFFFFFu;  // lane j: posting word of the tie signature when it belongs to run j
+
+        // f32 filter constants from (Sk, tie signature, pruned set)
+        auto refresh_filter = [&]() {
+            f.tie_dk = (f.tie_sig != SIG_NONE && ne_mask == 0u) ? f.dk : INF;  // pruned terms: no tie shortcut
+            const double flo = f.Sk * (1.0 - kEps) - ub_ne;
+            f.Flo = __double2float_rd(flo);
+            // F = s0·tf/(tf+s1) >= flo  ⇔  tf >= flo/(s0-flo)·s1  (s0 > flo), never when s0 <= flo.  Solved in f64
+            // from the exact s0, shrunk by 2^-20 to stay conservative in f32.
+            f.ctf = __int_as_float(0x7f800000);  // +inf
+            if (lane < (int)m && s0d > flo) f.ctf = __double2float_rd(flo / (s0d - flo) * (1.0 - 1.0 / 1048576.0));
+            // one-compare version for the hot loop: tf >= ctf·s1[fn] needs tf >= floor(ctf · min s1)
+            uint32_t tfmin = 0x1000000u;
+            if (f.ctf < 3.0e38f) {
+                const float t = f.ctf * s1min;
+                tfmin = t < 16777216.f ? (t > 1.f ? (uint32_t)t : 1u) : 0x1000000u;
+            }
+            wlim = tfmin >= 0x1000000u ? 0xFFFFFFFFu : (tfmin << 8) - 1u;
+            tiew = (f.tie_dk != INF && (f.tie_sig >> 27) == (uint32_t)lane) ? (f.tie_sig & 0x07FFFFFFu) : 0xFFFFFFFFu;
+        };
+        // cut the pool back to k and refresh the threshold (Results::push / threshold, search.rs:284-314)
+        auto pool_cut = [&]() {
+            wpool_sort<C>(pl, pn, lane);
+            if (pn > (int)k) pn = (int)k;
+            if (pn == (int)k) {
+                f.Sk = __longlong_as_double((long long)pl.s[k - 1]);
+                f.dk = pl.d[k - 1];
+                f.tie_sig = pl.g[k - 1];
+                f.tv = true;
+                thr_new = true;
+                refresh_filter();
+            }
+        };
+
+        // one refill round: lane j appends n postings (even) to its ring
+        auto issue_round = [&](uint32_t n) -> bool {
+            const uint32_t total = __reduce_add_sync(FULL, n);
+            if (total == 0u) return false;
+            // the freed ring slots were last read through the generic proxy by this warp: order those reads before the
+            // async-proxy writes
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive_expect_tx(bar, total * (uint32_t)sizeof(Posting));
+            __syncwarp();
+            if (n > 0) {
+                const uint32_t off = wr & C::RM;
+                const uint32_t n1 = min(n, (uint32_t)C::R - off);
+                const Posting *src = p.post + pbase + wr;
+                tma_load_1d(myring + off, src, n1 * (uint32_t)sizeof(Posting), bar);
+                if (n > n1) tma_load_1d(myring, src + n1, (n - n1) * (uint32_t)sizeof(Posting), bar);
+                fetched += min(wr + n, dfj) - min(wr, dfj);  // the pad slot of an odd list is not a posting
+                wr += n;
+            }
+            return true;
+        };
+
+        bool inflight = issue_round(lane < (int)m ? min(dfpad, (uint32_t)C::INIT) : 0u);
+#ifdef BM25X_WATCHDOG
+        uint32_t wd_chunks = 0;
+#endif
+        for (;;) {
+#ifdef BM25X_WATCHDOG
+            if (++wd_chunks > (1u << 26)) __trap();  // debug builds: a query that never ends becomes a launch failure
+#endif
+            // ---- chunk boundary: the outstanding round has landed ----
+            if (inflight) {
+                mbar_wait(bar, parity);
+                parity ^= 1u;
+            }
+            // MaxScore: move the terms with the smallest score bounds out of the streamed set while the sum of their
+            // bounds stays below 5 % of the k-th score (a document holding only such terms cannot enter; for the
+            // others the bound is added back in the filter and the exact contribution is probed at verification).
+            // Only at chunk boundaries: inside a chunk the "last holder emits" rule relies on a fixed streamed set.
+            if (p.prune && thr_new) {
+                thr_new = false;
+                bool changed = false;
+                for (;;) {
+                    const bool ess = lane < (int)m && !((ne_mask >> lane) & 1u);
+                    unsigned long long key = ess ? (unsigned long long)__double_as_longlong(ubd) : ~0ull;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const unsigned long long other = __shfl_xor_sync(FULL, key, o);
+                        key = other < key ? other : key;
+                    }
+                    const uint32_t who = __ballot_sync(FULL, ess && (unsigned long long)__double_as_longlong(ubd) == key);
+                    const uint32_t ness = __popc(__ballot_sync(FULL, ess));
+                    if (who == 0u || ness <= 1u) break;
+                    const double ub = __longlong_as_double((long long)key);
+                    if (!(ub_ne + ub <= 0.05 * f.Sk)) break;
+                    ne_mask |= 1u << (__ffs(who) - 1);
+                    ub_ne += ub;
+                    changed = true;
+                }
+                if (changed) refresh_filter();
+            }
+            const bool act = lane < (int)m && !((ne_mask >> lane) & 1u);
+            const uint32_t avail_e = min(wr, dfj);
+            uint32_t limit = INF;  // runs with postings left in HBM bound the window by their last landed document
+            if (act && wr < dfj) limit = myring[(wr - 1u) & C::RM].doc;
+            uint32_t hi = __reduce_min_sync(FULL, limit);
+            bool last = hi == INF;
+            uint32_t e = rd;
+            if (act) e = last ? avail_e : ring_lower_bound<C>(myring, rd, avail_e, hi);
+            // ---- dense or sparse?  (expected number of documents held by two runs in this window) ----
+            bool dense = false;
+            uint32_t span = 0;
+            if (C::M > 1) {
+                const uint32_t n = e - rd;
+                const uint32_t S = __reduce_add_sync(FULL, n);
+                const uint32_t S2 = __reduce_add_sync(FULL, n * n);
+                uint32_t hi_eff = hi;
+                if (last) hi_eff = __reduce_max_sync(FULL, n ? myring[(e - 1u) & C::RM].doc + 1u : 0u);
+                span = hi_eff > lo ? hi_eff - lo : 0u;
+                dense = (unsigned long long)S * S - S2 > 2ull * BM25X_RING_DENSE_T * (unsigned long long)span;
+                if (dense && span > C::ACC_DOCS) {  // clamp the window to the accumulator: consume the rings partially
+                    hi = lo + C::ACC_DOCS;
+                    last = false;
+                    span = C::ACC_DOCS;
+                    if (act) e = ring_lower_bound<C>(myring, rd, e, hi);
+                }
+            }
+            // ---- refill: append what earlier chunks consumed (at most half a ring per round) ----
+            {
+                uint32_t n = 0;
+                if (act && wr < dfpad) {
+                    const uint32_t fr = (uint32_t)C::R - (wr - rd);
+                    n = min(min(fr, (uint32_t)C::R / 2) & ~1u, dfpad - wr);
+                    // no small top-ups while the run still holds a quarter ring beyond this chunk
+                    if (n < (uint32_t)C::R / 8 && wr - e >= (uint32_t)C::R / 4) n = 0;
+                }
+                inflight = issue_round(n);
+            }
+
+            uint32_t nc = 0;  // listed candidates (warp-uniform)
+            // ---- verification: 32 listed postings at a time ----
+            auto verify = [&]() {
+                for (uint32_t base = 0; base < nc; base += 32) {
+                    const bool has = base + lane < nc;
+                    const uint32_t ent = has ? cand[base + lane] : 0u;
+                    const bool by_doc = (ent >> 31) != 0u;            // dense flavour: document given as offset from lo
+                    const uint32_t j = by_doc ? 32u : (ent >> 16) & 31u;
+                    Posting own;
+                    own.doc = 0;
+                    own.w = 0;
+                    if (has && !by_doc) own = rings[(size_t)j * C::R + (ent & 0xFFFFu)];
+                    const uint32_t doc = by_doc ? lo + (ent & 0x7FFFFFFFu) : own.doc;
+                    float F = 0.f;
+                    uint32_t cnt = 0, sig = SIG_NONE;
+                    bool later = false;
+                    constexpr bool KEEPW = C::M <= 8;  // posting words of the holders stay in registers for the exact pass
+                    uint32_t wv[KEEPW ? C::M : 1];
+#pragma unroll
+                    for (int i = 0; i < (KEEPW ? C::M : 1); ++i) wv[i] = 0u;
+                    auto holder = [&](int i, uint32_t ai, uint32_t ei) -> uint32_t {
+                        return (uint32_t)i == j ? own.w : ring_find<C>(rings + (size_t)i * C::R, ai, ei, doc);
+                    };
+                    auto filter_term = [&](int i) {
+                        const uint32_t ai = __shfl_sync(FULL, rd, i), ei = __shfl_sync(FULL, e, i);
+                        const float s0 = __shfl_sync(FULL, s0f, i);
+                        uint32_t wi = 0u;
+                        if (has && !((ne_mask >> i) & 1u)) {
+                            wi = holder(i, ai, ei);
+                            if (wi) {
+                                F += score_f32(wi, s0, s1f);
+                                cnt++;
+                                sig = make_sig(i, wi);
+                                later |= (uint32_t)i > j;
+                            }
+                        }
+                        return wi;
+                    };
+                    if constexpr (KEEPW) {
+#pragma unroll
+                        for (int i = 0; i < C::M; ++i)
+                            if (i < (int)m) wv[i] = filter_term(i);
+                    } else {
+#pragma unroll 1
+                        for (int i = 0; i < (int)m; ++i) filter_term(i);
+                    }
+                    // the last streamed run holding the document emits it: its posting always detects the others
+                    bool keep = has && !later && wfilter_pass(f, F, cnt == 1 ? sig : SIG_NONE, doc);
+                    if (keep && p.allow && !((p.allow[doc >> 3] >> (doc & 7u)) & 1u)) keep = false;
+                    if (__any_sync(FULL, keep)) {
+                        // exact re-score in the reference's operation order; pruned terms are probed in HBM
+                        double Sx = 0.0;
+                        uint32_t cnt_all = 0;
+                        auto exact_term = [&](int i, uint32_t wi) {
+                            const double s0 = __shfl_sync(FULL, s0d, i);
+                            if ((ne_mask >> i) & 1u) {
+                                const uint64_t pb = __shfl_sync(FULL, pbase, i), bb = __shfl_sync(FULL, bbase, i);
+                                const uint32_t nbq = __shfl_sync(FULL, nbj, i), dfq = __shfl_sync(FULL, dfj, i);
+                                wi = 0u;
+                                if (keep) {
+                                    wi = probe_global(p, pb, bb, nbq, dfq, doc);
+                                    if (wi) sig = make_sig(i, wi);
+                                }
+                            }
+                            if (keep && wi) {
+                                Sx = __dadd_rn(Sx, score_f64(wi, s0, p.s1d));
+                                cnt_all++;
+                            }
+                        };
+                        if constexpr (KEEPW) {
+#pragma unroll
+                            for (int i = 0; i < C::M; ++i)
+                                if (i < (int)m) exact_term(i, wv[i]);
+                        } else {
+#pragma unroll 1
+                            for (int i = 0; i < (int)m; ++i) {
+                                const uint32_t ai = __shfl_sync(FULL, rd, i), ei = __shfl_sync(FULL, e, i);
+                                uint32_t wi = 0u;
+                                if (keep && !((ne_mask >> i) & 1u)) wi = holder(i, ai, ei);
+                                exact_term(i, wi);
+                            }
+                        }
+                        keep = keep && (!f.tv || Sx > f.Sk || (Sx == f.Sk && doc < f.dk));
+                        const uint32_t mk = __ballot_sync(FULL, keep);
+                        if (keep) {
+                            const int idx = pn + __popc(mk & lt_mask);
+                            pl.s[idx] = (uint64_t)__double_as_longlong(Sx);
+                            pl.d[idx] = doc;
+                            pl.g[idx] = cnt_all == 1 ? sig : SIG_NONE;
+                        }
+                        pn += __popc(mk);
+                        __syncwarp();
+                        // Re-sorting a large pool is expensive (bitonic sort of KP entries): once a threshold exists,
+                        // the big pool is cut only when it is about to overflow.
+                        const bool lazy = C::KP > 128 && f.tv;
+                        if (pn > C::KP - 32 || (!lazy && pn >= (int)k + 32)) pool_cut();
+                    }
+                }
+                nc = 0;
+            };
+
+            if (!dense) {
+                // ---- sparse window: runs in ascending order; test against the marks of the earlier runs, then mark ----
+                const uint32_t nonempty = __ballot_sync(FULL, act && e > rd);
+                const bool multi = C::M > 1 && __popc(nonempty) > 1;
+                if (multi) gen = gen % 255u + 1u;
+                const uint32_t genv = gen;
+                uint32_t todo = nonempty;
+                bool first = true;
+                while (todo) {
+                    const int j = __ffs(todo) - 1;
+                    todo &= todo - 1u;
+                    const uint32_t a = __shfl_sync(FULL, rd, j), ee = __shfl_sync(FULL, e, j);
+                    const uint32_t wl = __shfl_sync(FULL, wlim, j), tw = __shfl_sync(FULL, tiew, j);
+                    const uint32_t nj = ee - a;
+                    const uint4 *rg = (const uint4 *)(rings + (size_t)j * C::R);
+                    const uint32_t tdk = f.tie_dk;  // snapshot with tw: a stale (looser) pair stays valid, thresholds only tighten
+                    uint32_t pb = a & ~1u;
+                    // trips of TRIP postings until the run is done or the candidate list wants to be verified
+                    auto run = [&](auto test_c, auto mark_c) {
+                        constexpr bool TEST = decltype(test_c)::value, MARK = decltype(mark_c)::value;
+                        for (; pb < ee && nc <= 64u; pb += C::TRIP) {
+                            uint4 q[C::U];
+                            uint32_t ix[C::U];
+#pragma unroll
+                            for (int u = 0; u < C::U; ++u) {
+                                ix[u] = pb + 2u * (uint32_t)(lane + 32 * u);
+                                q[u] = rg[(ix[u] >> 1) & (C::RM >> 1)];
+                            }
+                            bool c[2 * C::U];
+                            bool anyc = false;
+#pragma unroll
+                            for (int u = 0; u < C::U; ++u) {
+#pragma unroll
+                                for (int h = 0; h < 2; ++h) {
+                                    const uint32_t doc = h ? q[u].z : q[u].x, w = h ? q[u].w : q[u].y;
+                                    const bool valid = ix[u] + h - a < nj;  // unsigned: also false below a
+                                    bool hit = false;
+                                    if (TEST || MARK) {
+                                        const uint32_t slot = ring_slot(doc, C::LOG_S);
+                                        if (TEST) hit = map[slot] == genv;
+                                        if (MARK && valid) map[slot] = (uint8_t)genv;
+                                    }
+                                    const bool solo = w > wl && !(w == tw && doc > tdk);
+                                    c[2 * u + h] = valid && (hit || solo);
+                                    anyc |= c[2 * u + h];
+                                }
+                            }
+                            if (__any_sync(FULL, anyc)) {
+#pragma unroll
+                                for (int u = 0; u < C::U; ++u) {
+#pragma unroll
+                                    for (int h = 0; h < 2; ++h) {
+                                        const uint32_t mc = __ballot_sync(FULL, c[2 * u + h]);
+                                        if (c[2 * u + h])
+                                            cand[nc + __popc(mc & lt_mask)] = ((uint32_t)j << 16) | ((ix[u] + h) & C::RM);
+                                        nc += __popc(mc);
+                                    }
+                                }
+                                __syncwarp();
+                            }
+                        }
+                    };
+                    const bool mark = multi && todo != 0u, test = multi && !first;
+                    for (;;) {
+                        if (test && mark) run(std::true_type(), std::true_type());
+                        else if (mark) run(std::false_type(), std::true_type());
+                        else if (test) run(std::true_type(), std::false_type());
+                        else run(std::false_type(), std::false_type());
+                        if (pb >= ee) break;
+                        verify();  // the list is full: settle it, then resume this run
+                    }
+                    first = false;
+                    __syncwarp();  // this run's marks are visible to the next run's tests
+                }
+            } else {
+                // ---- dense window: scores summed in an f32 accumulator indexed by doc - lo (in the map's memory;
+                // docs are distinct inside a run: plain read-modify-write, __syncwarp between runs) ----
+                float *acc = (float *)map;
+                for (uint32_t i = lane; i < (span + 3u) / 4u; i += 32) ((float4 *)acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                __syncwarp();
+                uint32_t todo = __ballot_sync(FULL, act && e > rd);
+                while (todo) {
+                    const int j = __ffs(todo) - 1;
+                    todo &= todo - 1u;
+                    const uint32_t a = __shfl_sync(FULL, rd, j), ee = __shfl_sync(FULL, e, j);
+                    const float s0 = __shfl_sync(FULL, s0f, j);
+                    const Posting *rg = rings + (size_t)j * C::R;
+                    for (uint32_t i = a + lane; i < ee; i += 32) {
+                        const Posting v = rg[i & C::RM];
+                        acc[v.doc - lo] += score_f32(v.w, s0, s1f);
+                    }
+                    __syncwarp();
+                }
+                for (uint32_t base = 0; base < span; base += 32) {
+                    const uint32_t o = base + lane;
+                    const float F = o < span ? acc[o] : 0.f;
+                    const bool c = F > 0.f && F >= f.Flo;
+                    const uint32_t mc = __ballot_sync(FULL, c);
+                    if (mc) {
+                        if (c) cand[nc + __popc(mc & lt_mask)] = 0x80000000u | o;
+                        nc += __popc(mc);
+                        __syncwarp();
+                        if (nc > 64u) verify();
+                    }
+                }
+            }
+            if (nc) verify();
+            rd = e;
+            lo = hi;
+            if (last) break;
+        }
+        // ---- Results::into_sorted_vec (search.rs:281) ----
+        if (pn > 0) pool_cut();
+        const size_t obase = (size_t)qid * k;
+        for (uint32_t i = lane; i < k; i += 32) {
+            uint32_t d = INF;
+            double sc = 0.0;
+            if ((int)i < pn) {
+                d = pl.d[i];
+                sc = __longlong_as_double((long long)pl.s[i]);
+            }
+            p.out_doc[obase + i] = d;
+            p.out_score[obase + i] = (float)sc;
+            if (p.out_score64) p.out_score64[obase + i] = sc;
+            if (p.out_payload) {
+                uint16_t a = 0, b = 0, cc = 0;
+                if ((int)i < pn) {
+                    a = p.payload[(size_t)d * 3 + 0];
+                    b = p.payload[(size_t)d * 3 + 1];
+                    cc = p.payload[(size_t)d * 3 + 2];
+                }
+                p.out_payload[(obase + i) * 3 + 0] = a;
+                p.out_payload[(obase + i) * 3 + 1] = b;
+                p.out_payload[(obase + i) * 3 + 2] = cc;
+            }
+        }
+        if (lane == 0) p.out_n[qid] = (uint32_t)pn;
+        if (p.fetched) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) fetched += __shfl_xor_sync(FULL, fetched, o);
+            if (lane == 0) atomicAdd(p.fetched, fetched);
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace
