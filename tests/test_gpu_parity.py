@@ -185,24 +185,40 @@ def test_config2_sample_1M_docs(m, orc):
     ix.close()
 
 
-def test_config3_sample_10M_docs(m, orc):
-    """BASELINE config 3 shape at full size (10M docs, vocab 100k, 128 terms/doc): 3-term queries top-10 on the GPU;
-    every query checked for the size-independent properties, a sample checked bit for bit against the oracle."""
-    c = m.synth_corpus(0xB25C0DE3, 10_000_000, 100_000, 128)
-    q_off, q_terms = m.synth_queries(0xB25C0DE3 + 1000, 4000, 100_000, 3, 3, c.post_off)
-    ix = m.Index.from_corpus(c)
-    res = ix.search_batch(q_off, q_terms, 10)
-    assert np.all(res["n"] == 10)
-    s = res["score64"]
-    assert np.all(s[:, :-1] >= s[:, 1:])
-    tie = s[:, :-1] == s[:, 1:]
-    assert np.all(res["doc"][:, :-1][tie] < res["doc"][:, 1:][tie])
-    assert np.all(res["doc"] < 10_000_000)
-    assert all(len(set(r)) == 10 for r in res["doc"][::50].tolist())            # no document twice
+def test_lookup_terms_16_byte_keys_then_search(m, orc):
+    """address_tokens::read (crates/bm25/src/address_tokens.rs:61-98) + the skip of unknown tokens (search.rs:55-62):
+    16-byte interned keys → term ordinals → search.  Short tokens are interned as their zero-padded bytes
+    (crates/bm25/src/vector.rs:19-24)."""
+    c = m.synth_corpus(81, 5000, 300, 8, 60, 0.5)
+    words = sorted(f"tok{i:05d}".encode() for i in range(300))           # strictly ascending byte strings
+    keys = np.zeros((300, 16), dtype=np.uint8)
+    for i, w in enumerate(words):
+        keys[i, :len(w)] = list(w)
+    ix = m.Index.from_corpus(c, term_keys=keys)
+    miss = np.zeros((2, 16), dtype=np.uint8)
+    miss[0, :5] = list(b"nope!")                                          # sorts after every key
+    miss[1, :3] = list(b"abc")                                            # sorts before every key
+    look = np.concatenate([keys[[5, 17, 299, 0]], miss])
+    ords = ix.lookup_terms(look)
+    assert ords.tolist() == [5, 17, 299, 0, m.TERM_MISSING, m.TERM_MISSING]
+    # a query in key space: unknown tokens are dropped, the rest searched — identical to the ordinal query
+    q_off = np.array([0, len(ords)], dtype=np.uint32)
+    res = ix.search_batch(q_off, ords, 10)
     oix = _oracle_index(orc, c)
-    idx = np.arange(0, 4000, 211)
-    sub_off = (3 * np.arange(len(idx) + 1)).astype(np.uint32)
-    sub_terms = np.concatenate([q_terms[q_off[i]:q_off[i + 1]] for i in idx])
-    sub = {k: (v[idx] if isinstance(v, np.ndarray) else v) for k, v in res.items()}
-    _compare(sub, oix, sub_off, sub_terms, 10, what="C3")
+    _compare(res, oix, np.array([0, 4], dtype=np.uint32), np.array([5, 17, 299, 0], dtype=np.uint32), 10, what="lookup")
     ix.close()
+    # keys must be strictly ascending (the reference's token address tree is sorted): rejected at create
+    bad = keys.copy()
+    bad[[10, 11]] = bad[[11, 10]]
+    with pytest.raises(m.Bm25xError) as e:
+        m.Index.from_corpus(c, term_keys=bad)
+    assert e.value.code == 1
+    dup = keys.copy()
+    dup[11] = dup[10]
+    with pytest.raises(m.Bm25xError):
+        m.Index.from_corpus(c, term_keys=dup)
+    # an index created without keys addresses terms by ordinal only
+    plain = m.Index.from_corpus(c)
+    with pytest.raises(m.Bm25xError, match="without term keys"):
+        plain.lookup_terms(keys[:1])
+    plain.close()

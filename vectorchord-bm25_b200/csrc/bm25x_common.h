@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -64,5 +65,11 @@ struct bm25x_index {
     std::vector<uint8_t> h_keys;       // [n_terms*16] sorted keys (optional)
     cudaStream_t stream = nullptr;
     std::vector<void *> allocs;
-    int prune = 1;                     // MaxScore-style pruning in k_search_wq
+    int prune = 1;                     // MaxScore-style pruning in the search kernels
+    // page-locked staging buffer of bm25x_batch_prepare (grow-only, shared by the batches of this index)
+    uint32_t *h_stage = nullptr;
+    size_t h_stage_words = 0;
+    cudaEvent_t h_stage_free = nullptr;  // recorded after the upload that last read h_stage
+    bool h_stage_busy = false;
+    std::mutex stage_mutex;
 };

@@ -698,7 +698,10 @@ extern "C" int bm25x_growing_create(const bm25x_index *sealed, const bm25x_growi
 extern "C" void bm25x_index_destroy(bm25x_index *ix) {
     if (!ix) return;
     cudaSetDevice(ix->device);
+    if (ix->stream) cudaStreamSynchronize(ix->stream);
     for (void *p : ix->allocs) cudaFree(p);
+    if (ix->h_stage) cudaFreeHost(ix->h_stage);
+    if (ix->h_stage_free) cudaEventDestroy(ix->h_stage_free);
     if (ix->stream) cudaStreamDestroy(ix->stream);
     delete ix;
 }

@@ -24,6 +24,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 #include <vector>
 
 #include "bm25x_common.h"
@@ -82,8 +83,7 @@ static const int kNumClasses = 7;
 struct Group {
     int M = 0;
     uint32_t nq = 0;
-    std::vector<uint32_t> h_ids, h_off, h_terms;
-    uint32_t *d_ids = nullptr, *d_off = nullptr, *d_terms = nullptr;
+    uint32_t *d_ids = nullptr, *d_off = nullptr, *d_terms = nullptr;  // slices of one device buffer
     int *d_counter = nullptr;
 };
 
@@ -100,7 +100,7 @@ struct bm25x_batch {
     unsigned long long *d_fetched = nullptr;
     uint64_t postings = 0, qterms = 0;
     uint32_t live = 0;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_ready = nullptr;
     std::vector<void *> allocs;
     void *last_stream = nullptr;
 };
@@ -187,6 +187,7 @@ extern "C" void bm25x_batch_destroy(bm25x_batch *b) {
     for (void *p : b->allocs) cudaFreeAsync(p, b->ix->stream);
     if (b->ev0) cudaEventDestroy(b->ev0);
     if (b->ev1) cudaEventDestroy(b->ev1);
+    if (b->ev_ready) cudaEventDestroy(b->ev_ready);
     delete b;
 }
 
@@ -199,6 +200,9 @@ extern "C" void bm25x_batch_destroy(bm25x_batch *b) {
         }                            \
     } while (0)
 
+// Canonicalises the queries (sort + dedup: datatype/tsvector.rs:96-105; unknown tokens dropped: search.rs:55-62), groups
+// them by term-count class and uploads everything with ONE copy from a page-locked staging buffer cached in the index
+// handle.  OpenMP over the queries; no per-query allocation.
 extern "C" int bm25x_batch_prepare(bm25x_index *ix, uint32_t nq, const uint32_t *q_off, const uint32_t *q_terms,
                                    uint32_t k, const uint8_t *allow, bm25x_batch **out) {
     if (!ix || !out || (nq && (!q_off || (!q_terms && q_off[nq] != 0)))) {
@@ -218,48 +222,81 @@ extern "C" int bm25x_batch_prepare(bm25x_index *ix, uint32_t nq, const uint32_t 
         bm25x_set_error("bm25x_batch_prepare: k=%u > BM25X_MAX_K=%d", k, BM25X_MAX_K);
         return BM25X_ERR_UNSUPPORTED;
     }
+    const uint32_t T = ix->d.n_terms;
+    const uint32_t *h_df = ix->h_df.data();
+    // ---- pass 1 (parallel): canonical terms of query i written in place of its raw terms (never longer) ----
+    const size_t n_raw = nq ? q_off[nq] : 0;
+    std::vector<uint32_t> canon(n_raw ? n_raw : 1);
+    std::vector<uint32_t> live(nq ? nq : 1);  // live terms of query i
+    int bad_query = -1, bad_kind = 0;
+#pragma omp parallel for schedule(static, 1024)
+    for (uint32_t i = 0; i < nq; ++i) {
+        if (q_off[i + 1] < q_off[i]) {
+#pragma omp critical
+            { bad_query = (int)i; bad_kind = 1; }
+            live[i] = 0;
+            continue;
+        }
+        uint32_t *dst = canon.data() + q_off[i];
+        const uint32_t n = q_off[i + 1] - q_off[i];
+        uint32_t m = 0;
+        for (uint32_t j = 0; j < n; ++j) {
+            const uint32_t t = q_terms[q_off[i] + j];
+            if (t < T && h_df[t] != 0) dst[m++] = t;
+        }
+        std::sort(dst, dst + m);
+        m = (uint32_t)(std::unique(dst, dst + m) - dst);
+        if (m > BM25X_MAX_QUERY_TERMS) {
+#pragma omp critical
+            { bad_query = (int)i; bad_kind = 2; }
+        }
+        live[i] = m;
+    }
+    if (bad_query >= 0) {
+        if (bad_kind == 1) {
+            bm25x_set_error("bm25x_batch_prepare: q_off not monotone at %d", bad_query);
+            return BM25X_ERR_INVALID;
+        }
+        bm25x_set_error("bm25x_batch_prepare: query %d has %u live terms > %d", bad_query, live[bad_query],
+                        BM25X_MAX_QUERY_TERMS);
+        return BM25X_ERR_UNSUPPORTED;
+    }
     bm25x_batch *b = new bm25x_batch();
     b->ix = ix;
     b->nq = nq;
     b->k = k;
-    for (int c = 0; c < kNumClasses; ++c) {
-        b->groups[c].M = kClasses[c];
-        b->groups[c].h_off.push_back(0);
+    // ---- slots: query i is the slot[i]-th query of its class, its terms start at tpos[i] inside the class ----
+    uint8_t cls_of[BM25X_MAX_QUERY_TERMS + 1];
+    for (int m = 0, c = 0; m <= BM25X_MAX_QUERY_TERMS; ++m) {
+        while (kClasses[c] < m) ++c;
+        cls_of[m] = (uint8_t)c;
     }
-    // canonicalise: sort + dedup (datatype/tsvector.rs:96-105), drop unknown tokens (search.rs:55-62)
-    std::vector<uint32_t> tmp;
-    const uint32_t T = ix->d.n_terms;
+    std::vector<uint32_t> slot(nq ? nq : 1), tpos(nq ? nq : 1);
+    uint32_t cnt_q[kNumClasses] = {0}, cnt_t[kNumClasses] = {0};
     for (uint32_t i = 0; i < nq; ++i) {
-        if (q_off[i + 1] < q_off[i]) {
-            bm25x_set_error("bm25x_batch_prepare: q_off not monotone at %u", i);
-            delete b;
-            return BM25X_ERR_INVALID;
-        }
-        tmp.assign(q_terms + q_off[i], q_terms + q_off[i + 1]);
-        std::sort(tmp.begin(), tmp.end());
-        tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
-        size_t m = 0;
-        for (uint32_t t : tmp)
-            if (t < T && ix->h_df[t] != 0) tmp[m++] = t;
-        tmp.resize(m);
-        if (m == 0) continue;
-        if (m > BM25X_MAX_QUERY_TERMS) {
-            bm25x_set_error("bm25x_batch_prepare: query %u has %zu live terms > %d", i, m, BM25X_MAX_QUERY_TERMS);
-            delete b;
-            return BM25X_ERR_UNSUPPORTED;
-        }
-        int c = 0;
-        while (kClasses[c] < (int)m) ++c;
-        Group &g = b->groups[c];
-        g.h_ids.push_back(i);
-        for (uint32_t t : tmp) {
-            g.h_terms.push_back(t);
-            b->postings += ix->h_df[t];
-        }
-        g.h_off.push_back((uint32_t)g.h_terms.size());
-        g.nq++;
+        const uint32_t m = live[i];
+        if (!m) continue;
+        const int c = cls_of[m];
+        slot[i] = cnt_q[c]++;
+        tpos[i] = cnt_t[c];
+        cnt_t[c] += m;
         b->qterms += m;
         b->live++;
+    }
+    // one staging / device buffer: per class [ids | off | terms | work counter]
+    size_t base_ids[kNumClasses], base_off[kNumClasses], base_terms[kNumClasses], base_cnt[kNumClasses], words = 0;
+    for (int c = 0; c < kNumClasses; ++c) {
+        Group &g = b->groups[c];
+        g.M = kClasses[c];
+        g.nq = cnt_q[c];
+        base_ids[c] = words;
+        words += cnt_q[c];
+        base_off[c] = words;
+        words += (size_t)cnt_q[c] + 1;
+        base_terms[c] = words;
+        words += cnt_t[c];
+        base_cnt[c] = words;
+        words += 1;
     }
     cudaError_t e = cudaSetDevice(ix->device);
     if (e != cudaSuccess) {
@@ -268,21 +305,66 @@ extern "C" int bm25x_batch_prepare(bm25x_index *ix, uint32_t nq, const uint32_t 
         return BM25X_ERR_CUDA;
     }
     cudaStream_t st = ix->stream;
+    std::lock_guard<std::mutex> stage_lock(ix->stage_mutex);  // the staging buffer is shared by the batches of this index
+    if (ix->h_stage_words < words) {
+        if (ix->h_stage) {
+            cudaStreamSynchronize(st);  // an earlier batch's upload may still read it
+            cudaFreeHost(ix->h_stage);
+        }
+        ix->h_stage = nullptr;
+        ix->h_stage_words = 0;
+        const size_t cap = words + words / 4 + 1024;
+        e = cudaMallocHost((void **)&ix->h_stage, cap * sizeof(uint32_t));
+        if (e != cudaSuccess) {
+            bm25x_set_error("bm25x_batch_prepare: page-locked staging buffer: %s", cudaGetErrorString(e));
+            delete b;
+            return BM25X_ERR_OOM;
+        }
+        ix->h_stage_words = cap;
+    } else if (ix->h_stage_busy) {
+        cudaEventSynchronize(ix->h_stage_free);  // the previous upload from this buffer has been issued; wait for it
+    }
+    uint32_t *hs = ix->h_stage;
+    for (int c = 0; c < kNumClasses; ++c) {
+        hs[base_off[c]] = 0;
+        hs[base_cnt[c]] = 0;
+    }
+    uint64_t postings = 0;
+    // ---- pass 2 (parallel): scatter into the staging buffer ----
+#pragma omp parallel for schedule(static, 1024) reduction(+ : postings)
+    for (uint32_t i = 0; i < nq; ++i) {
+        const uint32_t m = live[i];
+        if (!m) continue;
+        const int c = cls_of[m];
+        hs[base_ids[c] + slot[i]] = i;
+        hs[base_off[c] + slot[i] + 1] = tpos[i] + m;
+        const uint32_t *src = canon.data() + q_off[i];
+        uint32_t *dst = hs + base_terms[c] + tpos[i];
+        for (uint32_t j = 0; j < m; ++j) {
+            dst[j] = src[j];
+            postings += h_df[src[j]];
+        }
+    }
+    b->postings = postings;
+    uint32_t *d_q = nullptr;
+    BTRY(batch_alloc(b, &d_q, words));
+    e = cudaMemcpyAsync(d_q, hs, words * sizeof(uint32_t), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        if (!ix->h_stage_free) e = cudaEventCreateWithFlags(&ix->h_stage_free, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventRecord(ix->h_stage_free, st);
+        ix->h_stage_busy = true;
+    }
     for (int c = 0; c < kNumClasses; ++c) {
         Group &g = b->groups[c];
-        if (!g.nq) continue;
-        BTRY(batch_alloc(b, &g.d_ids, g.h_ids.size()));
-        BTRY(batch_alloc(b, &g.d_off, g.h_off.size()));
-        BTRY(batch_alloc(b, &g.d_terms, g.h_terms.size()));
-        BTRY(batch_alloc(b, &g.d_counter, 1));
-        cudaMemcpyAsync(g.d_ids, g.h_ids.data(), 4 * g.h_ids.size(), cudaMemcpyHostToDevice, st);
-        cudaMemcpyAsync(g.d_off, g.h_off.data(), 4 * g.h_off.size(), cudaMemcpyHostToDevice, st);
-        cudaMemcpyAsync(g.d_terms, g.h_terms.data(), 4 * g.h_terms.size(), cudaMemcpyHostToDevice, st);
+        g.d_ids = d_q + base_ids[c];
+        g.d_off = d_q + base_off[c];
+        g.d_terms = d_q + base_terms[c];
+        g.d_counter = (int *)(d_q + base_cnt[c]);
     }
-    if (allow) {
+    if (allow && e == cudaSuccess) {
         size_t nb = ((size_t)ix->d.n_docs + 7) / 8;
         BTRY(batch_alloc(b, &b->d_allow, nb));
-        cudaMemcpyAsync(b->d_allow, allow, nb, cudaMemcpyHostToDevice, st);
+        e = cudaMemcpyAsync(b->d_allow, allow, nb, cudaMemcpyHostToDevice, st);
     }
     size_t slots = (size_t)nq * k;
     if (slots == 0) slots = 1;
@@ -292,14 +374,16 @@ extern "C" int bm25x_batch_prepare(bm25x_index *ix, uint32_t nq, const uint32_t 
     BTRY(batch_alloc(b, &b->d_out_payload, slots * 3));
     BTRY(batch_alloc(b, &b->d_out_n, nq));
     BTRY(batch_alloc(b, &b->d_fetched, 1));
-    e = cudaMemsetAsync(b->d_out_n, 0, 4 * (size_t)(nq ? nq : 1), st);
-    if (e == cudaSuccess) e = cudaMemsetAsync(b->d_out_doc, 0xFF, 4 * (slots ? slots : 1), st);
-    if (e == cudaSuccess) e = cudaMemsetAsync(b->d_out_score, 0, 4 * (slots ? slots : 1), st);
-    if (e == cudaSuccess) e = cudaMemsetAsync(b->d_out_score64, 0, 8 * (slots ? slots : 1), st);
-    if (e == cudaSuccess) e = cudaMemsetAsync(b->d_out_payload, 0, 6 * (slots ? slots : 1), st);
+    // rows of queries without a live term are never written by a kernel
+    if (e == cudaSuccess) e = cudaMemsetAsync(b->d_out_n, 0, 4 * (size_t)(nq ? nq : 1), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(b->d_out_doc, 0xFF, 4 * slots, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(b->d_out_score, 0, 4 * slots, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(b->d_out_score64, 0, 8 * slots, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(b->d_out_payload, 0, 6 * slots, st);
     if (e == cudaSuccess) e = cudaEventCreate(&b->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&b->ev1);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_ready, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventRecord(b->ev_ready, st);  // bm25x_batch_run on another stream waits for the upload
     if (e != cudaSuccess) {
         bm25x_set_error("bm25x_batch_prepare: %s", cudaGetErrorString(e));
         bm25x_batch_destroy(b);
@@ -318,6 +402,7 @@ extern "C" int bm25x_batch_run(bm25x_batch *b, void *stream_v, bm25x_search_stat
     BM25X_CUDA_TRY(cudaSetDevice(ix->device));
     cudaStream_t st = stream_v ? (cudaStream_t)stream_v : ix->stream;
     b->last_stream = (void *)st;
+    if (st != ix->stream) BM25X_CUDA_TRY(cudaStreamWaitEvent(st, b->ev_ready, 0));  // uploads were issued on the library's stream
     const DeviceIndex &d = ix->d;
     uint32_t launches = 0;
     if (stats) {

@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                 span = hi_eff > lo ? hi_eff - lo : 0u;
                 dense = (unsigned long long)S * S - S2 > 2ull * BM25X_RING_DENSE_T * (unsigned long long)span;
                 if (dense && span > C::ACC_DOCS) {  // clamp the window to the accumulator: consume the rings partially
-                    hi = lo + C::ACC_DOCS;
+                    hi = lo < INF - 1u - C::ACC_DOCS ? lo + C::ACC_DOCS : INF - 1u;
                     last = false;
                     span = C::ACC_DOCS;
                     if (act) e = ring_lower_bound<C>(myring, rd, e, hi);
