@@ -65,7 +65,7 @@ typedef struct {
 
 typedef struct {
     double kernel_ms;        /* device time of the search kernels, CUDA events on the launch stream */
-    double h2d_ms, d2h_ms;   /* host-API variant only */
+    double h2d_ms, d2h_ms;   /* bm25x_search_batch only (host clock): canonicalise + upload, download of the results */
     uint64_t postings;       /* Σ df over live query terms (algorithmic postings touched, exhaustive) */
     uint64_t bytes_algo;     /* 8 B/posting + 8 B/result slot + 16 B/query term */
     uint32_t launches;       /* kernels launched */
@@ -105,6 +105,12 @@ typedef struct {
     const uint8_t *bytes;          /* concatenated block payloads */
     uint64_t n_bytes;
     double k1, b;
+    /* SummaryTuple.wand_fieldnorm / wand_term_frequency (tuples.rs:900-910; written by flush.rs:101-120): the arg-max
+     * posting of each block, whose score is the block's upper bound (search.rs:381,426-429).  Optional (both or
+     * neither): when given they are checked against the decoded postings ("corrupt blocks" on mismatch); the bounds
+     * the kernels use are always computed from the decoded postings themselves. */
+    const uint8_t *blk_wand_fieldnorm; /* [n_blocks] or NULL */
+    const uint32_t *blk_wand_tf;       /* [n_blocks] or NULL */
 } bm25x_blocks;
 int bm25x_index_create_from_blocks(const bm25x_blocks *blocks, int device, bm25x_index **out);
 
@@ -113,7 +119,7 @@ int bm25x_index_create_from_blocks(const bm25x_blocks *blocks, int device, bm25x
  * torch.distributed.broadcast over NVLink).  Sender: bm25x_index_get_layout.  Receiver: bm25x_index_alloc_replica
  * with the sender's layout (scalars only are read), fill the arrays named by its own layout, then
  * bm25x_index_finalize_replica. */
-#define BM25X_N_ARRAYS 12
+#define BM25X_N_ARRAYS 13
 typedef struct {
     uint32_t n_docs, n_terms;
     uint64_t n_postings, n_postings_padded, n_blocks, sum_doc_len;
@@ -136,6 +142,13 @@ int bm25x_index_get_df(const bm25x_index *idx, uint32_t *df_out);
 /* address_tokens::read (crates/bm25/src/address_tokens.rs:61-98): key → dense term ordinal,
  * BM25X_TERM_MISSING when absent (search.rs:60-62 then skips it).  Needs term_key at create time. */
 int bm25x_lookup_terms(const bm25x_index *idx, const uint8_t *keys, uint32_t n, uint32_t *ordinals_out);
+
+/* vector::intern (crates/bm25/src/vector.rs:19-35): the 16-byte key of a token under the index's 32-byte seed.  Tokens
+ * shorter than 16 bytes without a NUL byte are their own zero-padded key; all others are the first 16 bytes of
+ * blake3::keyed_hash(seed, token) with a zero last byte replaced by 1.  Host-only (no device involved). */
+int bm25x_intern(const uint8_t seed[32], const uint8_t *token, size_t len, uint8_t key_out[BM25X_KEY_WIDTH]);
+/* Test hook: first 16 bytes of BLAKE3 keyed_hash(key, data) without the interning rules (known-answer tests). */
+int bm25x_blake3_keyed16(const uint8_t key[32], const uint8_t *data, size_t len, uint8_t out[16]);
 
 /* ---- bm25::search (crates/bm25/src/search.rs:28-282) for a whole batch of queries, called where
  * DefaultBuilder::build calls it (src/index/bm25/scanners/default.rs:117-129).

@@ -1014,3 +1014,14 @@ int orc_synth_doc(uint64_t seed, uint32_t doc, uint32_t vocab, uint32_t len_min,
     *len_out = L;
     return n;
 }
+
+/* SummaryTuple.{wand_fieldnorm, wand_term_frequency} of every block, in (token, block) order — what flush() stores
+ * next to min/max_document_id (flush.rs:101-120, tuples.rs:900-910). */
+void orc_index_block_wand(const orc_index *ix, uint8_t *fn_out, uint32_t *tf_out) {
+    const uint64_t n = ix->sum_off[ix->n_terms];
+    for (uint64_t i = 0; i < n; i++) {
+        fn_out[i] = ix->summaries[i].wand_fn;
+        tf_out[i] = ix->summaries[i].wand_tf;
+    }
+}
+uint64_t orc_index_n_blocks(const orc_index *ix) { return ix->sum_off[ix->n_terms]; }

@@ -107,6 +107,10 @@ int orc_search_growing(const orc_index *idx, uint32_t n_growing, const uint8_t *
                        const uint32_t *terms, int nterms, int k, const uint8_t *allow, uint32_t *out_doc,
                        double *out_score);
 
+/* SummaryTuple.{wand_fieldnorm, wand_term_frequency} of every 128-posting block, (token, block) order (flush.rs:101-120) */
+void orc_index_block_wand(const orc_index *idx, uint8_t *fn_out, uint32_t *tf_out);
+uint64_t orc_index_n_blocks(const orc_index *idx);
+
 /* ---- synthetic corpus spec (ours; mirrors tests/fuzz:168-205) ---- */
 uint64_t orc_splitmix64(uint64_t x);
 /* Build the integer inverse-CDF thresholds for Zipf(s) over `vocab` ranks

@@ -88,6 +88,10 @@ def lib():
     L.orc_draw.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32]
     L.orc_draw_term.restype = C.c_uint32
     L.orc_draw_term.argtypes = [C.c_uint64, C.c_uint32, u64p]
+    L.orc_index_block_wand.restype = None
+    L.orc_index_block_wand.argtypes = [C.c_void_p, u8p, u32p]
+    L.orc_index_n_blocks.restype = C.c_uint64
+    L.orc_index_n_blocks.argtypes = [C.c_void_p]
     L.orc_synth_corpus.restype = C.c_int
     L.orc_synth_corpus.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_double, C.c_int, u32p,
                                    u64p, u32p, u32p, C.c_uint64, u64p]
@@ -223,6 +227,14 @@ class OracleIndex:
             self.h = None
 
     @property
+    def block_wand(self):
+        """(wand_fieldnorm u8[], wand_term_frequency u32[]) of every block, (token, block) order (flush.rs:101-120)."""
+        n = int(lib().orc_index_n_blocks(self.h))
+        fn = np.zeros(max(n, 1), dtype=np.uint8)
+        tf = np.zeros(max(n, 1), dtype=np.uint32)
+        lib().orc_index_block_wand(self.h, _p(fn, C.c_uint8), _p(tf, C.c_uint32))
+        return fn[:n], tf[:n]
+
     def avgdl(self):
         return lib().orc_index_avgdl(self.h)
 

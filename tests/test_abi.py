@@ -99,7 +99,7 @@ def test_struct_layouts_match_the_header(m):
                "bm25x_blocks": (bm._Blocks, ["n_docs", "doc_len", "doc_fieldnorm", "sum_doc_len", "payload", "n_terms",
                                              "term_key", "term_blk_off", "n_blocks", "blk_min_doc", "blk_n",
                                              "blk_meta_doc", "blk_meta_tf", "blk_doc_off", "blk_tf_off", "bytes",
-                                             "n_bytes", "k1", "b"]),
+                                             "n_bytes", "k1", "b", "blk_wand_fieldnorm", "blk_wand_tf"]),
                "bm25x_index_info": (bm.IndexInfo, ["n_docs", "n_terms", "n_postings", "sum_doc_len", "avgdl", "k1", "b",
                                                    "device_bytes", "n_blocks", "device"]),
                "bm25x_index_layout": (bm.IndexLayout, ["n_docs", "n_terms", "n_postings", "n_postings_padded",

@@ -2,7 +2,7 @@
 
 The oracle's codec restatement (oracle/bm25_codec.c, pinned in tests/test_codec.py) encodes a corpus the way flush.rs
 does; the product decodes the blocks on the GPU.  Bar: the decoded index is byte-identical to the one built from the
-plain postings (all 12 device arrays), and searches on it are bit-exact against the oracle."""
+plain postings (all 13 device arrays), and searches on it are bit-exact against the oracle."""
 import numpy as np
 import pytest
 
@@ -141,6 +141,34 @@ def test_blocks_bytewidth4_tail_is_raw(m, orc):
     order = np.lexsort((docs, -tfs.astype(np.int64)))               # equal norms: tf desc, then doc id asc
     assert got_d.tolist() == docs[order].tolist()
     ix.close()
+
+
+def test_blocks_summary_wand_bounds_are_checked(m, orc):
+    """SummaryTuple.(wand_fieldnorm, wand_term_frequency) (tuples.rs:900-910, written by flush.rs:101-120): the oracle's
+    flush restatement produces them; the ingest accepts the real ones and refuses a pair that is not the block's
+    arg-max.  The per-block score bounds of the resulting index equal those of the index built from plain postings
+    (device array 12, compared by test_blocks_index_identical_and_search_exact for every config)."""
+    c = m.synth_corpus(47, 6000, 60, 4, 120, 0.9)
+    oc = orc.Corpus(c.n_docs, c.doc_len, c.n_terms, c.post_off, c.post_doc, c.post_tf)
+    wfn, wtf = orc.OracleIndex(oc).block_wand()
+    eb, ix = _from_blocks(m, orc, c, blk_wand_fieldnorm=wfn, blk_wand_tf=wtf)
+    assert len(wfn) == eb.n_blocks == ix.info().n_blocks
+    plain = m.Index.from_corpus(c)
+    assert np.array_equal(_device_arrays(plain)[12], _device_arrays(ix)[12])
+    ub = _device_arrays(ix)[12].view(np.float32)
+    assert len(ub) == eb.n_blocks and np.all(ub > 0)
+    plain.close()
+    ix.close()
+    bad_tf = wtf.copy()
+    g = int(np.argmax(wtf))               # a block whose arg-max has tf > 1: halving it lowers the bound
+    assert bad_tf[g] > 1
+    bad_tf[g] = 1
+    with pytest.raises(m.Bm25xError, match="wand"):
+        _from_blocks(m, orc, c, blk_wand_fieldnorm=wfn, blk_wand_tf=bad_tf)
+    bad_fn = wfn.copy()
+    bad_fn[0] = 255 if wfn[0] < 200 else 0   # a very different length norm
+    with pytest.raises(m.Bm25xError, match="wand"):
+        _from_blocks(m, orc, c, blk_wand_fieldnorm=bad_fn, blk_wand_tf=wtf)
 
 
 def test_blocks_corruption_is_reported(m, orc):

@@ -36,7 +36,8 @@ class _Blocks(C.Structure):
                 ("blk_min_doc", C.POINTER(C.c_uint32)), ("blk_n", C.POINTER(C.c_uint32)),
                 ("blk_meta_doc", C.POINTER(C.c_uint8)), ("blk_meta_tf", C.POINTER(C.c_uint8)),
                 ("blk_doc_off", C.POINTER(C.c_uint64)), ("blk_tf_off", C.POINTER(C.c_uint64)),
-                ("bytes", C.POINTER(C.c_uint8)), ("n_bytes", C.c_uint64), ("k1", C.c_double), ("b", C.c_double)]
+                ("bytes", C.POINTER(C.c_uint8)), ("n_bytes", C.c_uint64), ("k1", C.c_double), ("b", C.c_double),
+                ("blk_wand_fieldnorm", C.POINTER(C.c_uint8)), ("blk_wand_tf", C.POINTER(C.c_uint32))]
 
 
 class _GrowingDocs(C.Structure):
@@ -52,7 +53,7 @@ class IndexInfo(C.Structure):
                 ("device_bytes", C.c_uint64), ("n_blocks", C.c_uint64), ("device", C.c_int)]
 
 
-N_ARRAYS = 12
+N_ARRAYS = 13
 
 
 class IndexLayout(C.Structure):
@@ -127,10 +128,30 @@ def load_library():
     L.bm25x_synth_free.restype = None
     L.bm25x_synth_queries.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_double, u64p,
                                       u32p, u32p]
+    L.bm25x_intern.argtypes = [u8p, u8p, C.c_size_t, u8p]
+    L.bm25x_blake3_keyed16.argtypes = [u8p, u8p, C.c_size_t, u8p]
     L.bm25x_last_error.restype = C.c_char_p
     L.bm25x_device_count.restype = C.c_int
     _lib = L
     return L
+
+
+def intern(seed: bytes, token: bytes) -> bytes:
+    """vector::intern (crates/bm25/src/vector.rs:19-35): 16-byte key of a token under the index seed."""
+    assert len(seed) == 32
+    out = (C.c_uint8 * 16)()
+    sd = (C.c_uint8 * 32).from_buffer_copy(seed)
+    tk = (C.c_uint8 * max(len(token), 1)).from_buffer_copy(token if token else b"\0")
+    _check(load_library().bm25x_intern(sd, tk, len(token), out))
+    return bytes(out)
+
+
+def blake3_keyed16(key: bytes, data: bytes) -> bytes:
+    out = (C.c_uint8 * 16)()
+    kk = (C.c_uint8 * 32).from_buffer_copy(key)
+    dd = (C.c_uint8 * max(len(data), 1)).from_buffer_copy(data if data else b"\0")
+    _check(load_library().bm25x_blake3_keyed16(kk, dd, len(data), out))
+    return bytes(out)
 
 
 def _check(rc):
@@ -241,7 +262,7 @@ class Index:
     @classmethod
     def from_blocks(cls, n_docs, n_terms, term_blk_off, blk_min_doc, blk_n, blk_meta_doc, blk_meta_tf, blk_doc_off,
                     blk_tf_off, data, doc_len=None, doc_fieldnorm=None, sum_doc_len=0, k1=1.2, b=0.75, payload=None,
-                    term_keys=None, device=0) -> "Index":
+                    term_keys=None, device=0, blk_wand_fieldnorm=None, blk_wand_tf=None) -> "Index":
         """Index from the sealed segment as the reference stores it: per-token chains of 128-posting blocks in the
         codec of compression.rs, decoded on the GPU (bm25x_index_create_from_blocks).  Document norms come either from
         exact lengths (`doc_len`) or, as on the pages, from `doc_fieldnorm` + `sum_doc_len`."""
@@ -274,6 +295,9 @@ class Index:
         c.blk_tf_off = arr(blk_tf_off, np.uint64, C.c_uint64)
         c.bytes = arr(data, np.uint8, C.c_uint8)
         c.n_bytes = len(keep[-1])
+        if blk_wand_fieldnorm is not None and blk_wand_tf is not None:   # SummaryTuple.wand_* (checked against the blocks)
+            c.blk_wand_fieldnorm = arr(blk_wand_fieldnorm, np.uint8, C.c_uint8)
+            c.blk_wand_tf = arr(blk_wand_tf, np.uint32, C.c_uint32)
         h = C.c_void_p()
         _check(L.bm25x_index_create_from_blocks(C.byref(c), device, C.byref(h)))
         return cls._adopt(h, n_docs, n_terms)

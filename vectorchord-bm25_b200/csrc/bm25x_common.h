@@ -44,6 +44,7 @@ struct DeviceIndex {
     uint32_t *df = nullptr;         // [n_terms] TokenTuple.number_of_documents
     uint64_t *blk_off = nullptr;    // [n_terms+1] first block index of each term
     uint2 *blk = nullptr;           // [n_blocks] (first doc, last doc) — SummaryTuple.{min,max}_document_id
+    float *blk_ub = nullptr;        // [n_blocks] upper bound of one posting's score inside the block (SummaryTuple.wand_*)
     float *s0f = nullptr;           // [n_terms] float(s0)
     double *s0d = nullptr;          // [n_terms] idf*(k1+1), bm25.rs:348
     double *s1d = nullptr;          // [256] k1*(1-b+b*len(fn)/avgdl), bm25.rs:349-352

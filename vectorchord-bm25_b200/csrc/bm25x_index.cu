@@ -104,9 +104,14 @@ __global__ void k_pad_slots(const uint64_t *__restrict__ off_pad, const uint32_t
     }
 }
 
+// Per 128-posting block: (first doc, last doc) = SummaryTuple.{min,max}_document_id, and the block's score bound =
+// Cache::evaluate of the block's arg-max posting, what the reference keeps as SummaryTuple.(wand_fieldnorm,
+// wand_term_frequency) (flush.rs:101-120) and evaluates per block at query time (search.rs:381,426-429).  Stored as f32
+// rounded UP after the same 2^-40 inflation as the token-level bound.
 __global__ void k_block_desc(const uint64_t *__restrict__ off_pad, const uint32_t *__restrict__ df,
                              const uint64_t *__restrict__ blk_off, uint32_t n_terms, uint64_t n_blocks,
-                             const Posting *__restrict__ post, uint2 *__restrict__ blk) {
+                             const Posting *__restrict__ post, const double *__restrict__ s0d,
+                             const double *__restrict__ s1d, uint2 *__restrict__ blk, float *__restrict__ blk_ub) {
     uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n_blocks) return;
     uint32_t lo = 0, hi = n_terms;
@@ -120,6 +125,36 @@ __global__ void k_block_desc(const uint64_t *__restrict__ off_pad, const uint32_
     uint64_t last = first + BM25X_BLOCK;
     if (last > df[lo]) last = df[lo];
     blk[g] = make_uint2(post[off_pad[lo] + first].doc, post[off_pad[lo] + last - 1].doc);
+    const double s0 = s0d[lo];
+    double best = 0.0;
+    for (uint64_t i = first; i < last; i++) {
+        const uint32_t w = post[off_pad[lo] + i].w;
+        const double tfd = (double)(w >> 8);
+        const double v = __ddiv_rn(__dmul_rn(tfd, s0), __dadd_rn(tfd, s1d[w & 0xFFu]));
+        best = v > best ? v : best;
+    }
+    blk_ub[g] = __double2float_ru(best * (1.0 + 9.094947017729282e-13));
+}
+
+// Ingest check: the stored SummaryTuple.(wand_fieldnorm, wand_term_frequency) of a block must evaluate to the block's
+// real maximum (it is the arg-max of the block's own postings, flush.rs:101-110); anything else is a corrupt index.
+__global__ void k_check_block_wand(uint64_t n_blocks, const uint64_t *__restrict__ blk_off, uint32_t n_terms,
+                                   const uint8_t *__restrict__ wand_fn, const uint32_t *__restrict__ wand_tf,
+                                   const double *__restrict__ s0d, const double *__restrict__ s1d,
+                                   const float *__restrict__ blk_ub, uint32_t *__restrict__ err) {
+    uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_blocks) return;
+    uint32_t lo = 0, hi = n_terms;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi + 1) >> 1;
+        if (blk_off[mid] <= g) lo = mid;
+        else hi = mid - 1;
+    }
+    const double tfd = (double)wand_tf[g];
+    const double v = __ddiv_rn(__dmul_rn(tfd, s0d[lo]), __dadd_rn(tfd, s1d[wand_fn[g]]));
+    const float ub = __double2float_ru(v * (1.0 + 9.094947017729282e-13));
+    // tf() and Cache::evaluate round differently: allow the last f32 ulp either way
+    if (!(ub <= blk_ub[g] * 1.0000003f && ub >= blk_ub[g] * 0.9999997f)) atomicOr(err, 8u);
 }
 
 // Per-term upper bound of a single posting's exact score: max over the term's postings of Cache::evaluate
@@ -317,6 +352,7 @@ static int index_begin(const BuildMeta &m, int device, bm25x_index **ixp) {
     TRY(dev_alloc(ix, &d.df, T));
     TRY(dev_alloc(ix, &d.blk_off, (size_t)T + 1));
     TRY(dev_alloc(ix, &d.blk, nb));
+    TRY(dev_alloc(ix, &d.blk_ub, nb));
     TRY(dev_alloc(ix, &d.s0f, T));
     TRY(dev_alloc(ix, &d.s0d, T));
     TRY(dev_alloc(ix, &d.s1d, 256));
@@ -363,7 +399,8 @@ static cudaError_t index_finish_device(bm25x_index *ix) {
         e = cudaGetLastError();
     }
     if (e == cudaSuccess && nb) {
-        k_block_desc<<<(unsigned)((nb + 255) / 256), 256>>>(d.post_off, d.df, d.blk_off, T, nb, d.post, d.blk);
+        k_block_desc<<<(unsigned)((nb + 255) / 256), 256>>>(d.post_off, d.df, d.blk_off, T, nb, d.post, d.s0d, d.s1d, d.blk,
+                                                            d.blk_ub);
         e = cudaGetLastError();
     }
     if (e == cudaSuccess && T) {
@@ -575,11 +612,24 @@ extern "C" int bm25x_index_create_from_blocks(const bm25x_blocks *c, int device,
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = index_finish_device(ix);
+    uint8_t *d_wfn = nullptr;
+    uint32_t *d_wtf = nullptr;
+    if (c->blk_wand_fieldnorm && c->blk_wand_tf) {  // the stored per-block bounds must be those of the decoded postings
+        up(&d_wfn, c->blk_wand_fieldnorm, NB);
+        up(&d_wtf, c->blk_wand_tf, NB);
+        if (e == cudaSuccess && NB) {
+            k_check_block_wand<<<(unsigned)((NB + 255) / 256), 256>>>(NB, d.blk_off, T, d_wfn, d_wtf, d.s0d, d.s1d, d.blk_ub,
+                                                                     d_err);
+            e = cudaGetLastError();
+        }
+    }
     if (e == cudaSuccess && NB > 1) {
         k_check_block_order<<<(unsigned)((NB + 255) / 256), 256>>>(d.blk_off, T, NB, d.blk, d_err);
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaMemcpy(&h_err, d_err, sizeof(h_err), cudaMemcpyDeviceToHost);
+    cudaFree(d_wfn);
+    cudaFree(d_wtf);
     cudaFree(d_tbo);
     cudaFree(d_min);
     cudaFree(d_n);
@@ -603,6 +653,11 @@ extern "C" int bm25x_index_create_from_blocks(const bm25x_blocks *c, int device,
         bm25x_set_error("%s: term frequency >= 2^24 is not supported by the packed posting layout", who);
         bm25x_index_destroy(ix);
         return BM25X_ERR_UNSUPPORTED;
+    }
+    if (h_err & 8u) {
+        bm25x_set_error("%s: corrupt blocks (SummaryTuple wand_fieldnorm/wand_term_frequency is not the block's maximum)", who);
+        bm25x_index_destroy(ix);
+        return BM25X_ERR_INVALID;
     }
     *out = ix;
     return BM25X_OK;
@@ -729,10 +784,10 @@ static void layout_arrays(const bm25x_index *ix, void **ptr, uint64_t *bytes) {
     const DeviceIndex &d = ix->d;
     const uint64_t T = d.n_terms, N = d.n_docs;
     void *p[BM25X_N_ARRAYS] = {d.post, d.post_off, d.df, d.blk_off, d.blk, d.s0f, d.s0d, d.s1d, d.s1f, d.fieldnorm, d.payload,
-                               d.ubd};
+                               d.ubd, d.blk_ub};
     uint64_t b[BM25X_N_ARRAYS] = {sizeof(Posting) * (d.n_post_pad + 2), 8 * (T + 1), 4 * (T ? T : 1), 8 * (T + 1),
                                   8 * (d.n_blocks ? d.n_blocks : 1), 4 * (T ? T : 1), 8 * (T ? T : 1), 8 * 256, 4 * 256,
-                                  N, 6 * N, 8 * (T ? T : 1)};
+                                  N, 6 * N, 8 * (T ? T : 1), 4 * (d.n_blocks ? d.n_blocks : 1)};
     for (int i = 0; i < BM25X_N_ARRAYS; i++) {
         ptr[i] = p[i];
         bytes[i] = b[i];
@@ -806,6 +861,7 @@ extern "C" int bm25x_index_alloc_replica(const bm25x_index_layout *like, int dev
     TRY(dev_alloc(ix, &d.df, T));
     TRY(dev_alloc(ix, &d.blk_off, T + 1));
     TRY(dev_alloc(ix, &d.blk, d.n_blocks));
+    TRY(dev_alloc(ix, &d.blk_ub, d.n_blocks));
     TRY(dev_alloc(ix, &d.s0f, T));
     TRY(dev_alloc(ix, &d.s0d, T));
     TRY(dev_alloc(ix, &d.s1d, 256));

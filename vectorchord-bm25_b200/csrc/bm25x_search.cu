@@ -24,6 +24,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <mutex>
 #include <vector>
 
@@ -506,12 +507,20 @@ extern "C" int bm25x_search_batch(bm25x_index *ix, uint32_t nq, const uint32_t *
                                   uint32_t k, const uint8_t *allow, uint32_t *out_doc, float *out_score,
                                   double *out_score64, uint16_t *out_payload, uint32_t *out_n,
                                   bm25x_search_stats *stats) {
+    using clk = std::chrono::steady_clock;
     bm25x_batch *b = nullptr;
+    const auto t0 = clk::now();
     int rc = bm25x_batch_prepare(ix, nq, q_off, q_terms, k, allow, &b);
     if (rc != BM25X_OK) return rc;
-    bm25x_search_stats local;
-    rc = bm25x_batch_run(b, nullptr, stats ? stats : &local);
+    if (stats) cudaStreamSynchronize(ix->stream);  // so that h2d_ms means what it says (costs nothing: run follows)
+    const auto t1 = clk::now();
+    rc = bm25x_batch_run(b, nullptr, stats);  // stats == NULL: asynchronous, the fetch below synchronises
+    const auto t2 = clk::now();
     if (rc == BM25X_OK) rc = bm25x_batch_fetch(b, out_doc, out_score, out_score64, out_payload, out_n);
+    if (stats && rc == BM25X_OK) {  // host-clock phases of this call: canonicalise + upload, download
+        stats->h2d_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+        stats->d2h_ms = std::chrono::duration<double, std::milli>(clk::now() - t2).count();
+    }
     bm25x_batch_destroy(b);
     return rc;
 }

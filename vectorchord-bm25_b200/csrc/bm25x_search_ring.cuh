@@ -196,10 +196,12 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
             // from the exact s0, shrunk by 2^-20 to stay conservative in f32.
             f.ctf = __int_as_float(0x7f800000);  // +inf
             if (lane < (int)m && s0d > flo) f.ctf = __double2float_rd(flo / (s0d - flo) * (1.0 - 1.0 / 1048576.0));
-            // one-compare version for the hot loop: tf >= ctf·s1[fn] needs tf >= floor(ctf · min s1)
+            // one-compare version for the hot loop: tf >= ctf·s1[fn] implies tf >= fl(ctf · min s1) (rounding is monotone),
+            // and tf is an integer: tf >= ceil(that).  (floor would let every tf = 1 posting of a term whose best
+            // single-term score is just below the threshold through to the verification.)
             uint32_t tfmin = 0x1000000u;
             if (f.ctf < 3.0e38f) {
-                const float t = f.ctf * s1min;
+                const float t = ceilf(f.ctf * s1min);
                 tfmin = t < 16777216.f ? (t > 1.f ? (uint32_t)t : 1u) : 0x1000000u;
             }
             wlim = tfmin >= 0x1000000u ? 0xFFFFFFFFu : (tfmin << 8) - 1u;
