@@ -34,8 +34,9 @@ WORKLOADS = {
                seed=0xB25C0DE0 + 1, desc="C1: 1k docs, 100 3-term queries"),
     "c4": dict(docs=10_000_000, vocab=100_000, doclen=128, queries=4_000, tmin=8, tmax=8, zipf=1.0, k=10,
                seed=0xB25C0DE0 + 4, desc="C4: 10M docs Zipf(1), 8-term queries (4000-query subset; --no-prune = exhaustive)"),
-    "c5": dict(docs=50_000_000, vocab=100_000, doclen=128, queries=100_000, tmin=1, tmax=8, zipf=0.0, k=10,
-               seed=0xB25C0DE0 + 5, desc="C5: 50M docs, mixed 1-8 term queries (per-GPU shard of the 1M batch)"),
+    "c5": dict(docs=50_000_000, vocab=100_000, doclen=128, queries=1_000_000, tmin=1, tmax=8, zipf=0.0, k=10,
+               seed=0xB25C0DE0 + 5, scaling="strong",
+               desc="C5: 50M docs replicated, ONE batch of 1M mixed 1-8 term queries sharded over the GPUs, top-10"),
 }
 
 
@@ -51,6 +52,7 @@ def parse():
     ap.add_argument("--k", type=int)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling side leg of the default run")
     ap.add_argument("--no-prune", action="store_true", help="disable MaxScore-style pruning (exhaustive streaming)")
     return ap.parse_args()
 
@@ -159,6 +161,70 @@ def cpu_reference(oix, q_off, q_terms, k, n, threads):
     return n / dt, n, dt, st
 
 
+STRONG_MIX_QUERIES = 400_000   # side leg of the default run: C5's query mix, strong scaling, on the corpus already in HBM
+
+
+def strong_leg(m, torch, dist, index, stream, q_off_all, q_terms_all, k, rank, world, local_rank, reps=3):
+    """Strong scaling with the gather INSIDE the clock (north_star: "per-GPU results are gathered on the host"):
+    one batch, contiguous query shards (shard.shard_queries), every rank answers its shard through the C ABI from
+    page-locked host buffers (canonicalise + H2D + kernels), the result rows travel GPU → GPU to rank 0 (one
+    dist.gather per array over NCCL/NVLink) and rank 0 copies the whole batch's rows to its page-locked host buffers.
+    Host clock, synchronize + barrier on both sides, max over ranks."""
+    from vectorchord_bm25_b200 import shard
+    nq_total = len(q_off_all) - 1
+    sub_off, sub_terms, lo, hi = shard.shard_queries(q_off_all, q_terms_all, rank, world)
+    n_local = hi - lo
+    dev = torch.device("cuda", local_rank)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    sub_off, sub_terms = pin(sub_off), pin(sub_terms)
+    widths = {"doc": 4 * k, "score": 4 * k, "n": 4}
+    host = {name: torch.empty((nq_total, w), dtype=torch.uint8, pin_memory=True) for name, w in widths.items()} \
+        if rank == 0 else None
+
+    def once():
+        t0 = time.perf_counter()
+        b = index.prepare(sub_off, sub_terms, k)
+        b.run(stream=stream.cuda_stream, timed=False)
+        dr = b.device_results()
+        parts = {name: torch.as_tensor(shard._DevArray(*dr[name]), device=dev).view(n_local, widths[name])
+                 for name in widths}
+        stream.synchronize()
+        t1 = time.perf_counter()
+        g = shard.gather_rows(parts, nq_total, rank, world)
+        if rank == 0:
+            for name in widths:
+                host[name].copy_(g[name], non_blocking=True)
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        b.close()
+        return t1 - t0, t2 - t1
+
+    once()
+    times = []
+    for _ in range(reps):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        ts, tg = once()
+        if world > 1:
+            dist.barrier()
+        times.append((time.perf_counter() - t0, ts, tg))
+    t = torch.tensor(min(times), dtype=torch.float64, device=dev)   # best repetition of this rank ...
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)                     # ... slowest rank
+    total, ts, tg = (float(x) for x in t)
+    res = None
+    if rank == 0:
+        res = {"queries": nq_total, "value": nq_total / total, "unit": "queries/s", "ms": 1e3 * total,
+               "search_ms": 1e3 * ts, "gather_and_d2h_ms": 1e3 * tg, "n_gpus": world, "scaling": "strong",
+               "h2d_bytes": int(4 * (len(q_off_all) + len(q_terms_all))), "d2h_bytes": nq_total * (8 * k + 4),
+               "note": "one batch sharded over the ranks; rows gathered GPU->GPU to rank 0 (dist.gather, NCCL), then "
+                       "one D2H of the whole batch on rank 0; host clock, max over ranks",
+               "doc_sha": __import__("hashlib").sha256(host["doc"].numpy().tobytes()).hexdigest()[:16]}
+    return res
+
+
 def reference_arm(a, wl, k, cores, cores_how):
     """`--impl reference`: the reference's own CPU algorithm for this path (oracle/: Block-max WAND restatement, the
     reference itself is Rust + pgrx and cannot be built here) on the host cores.  Corpus and queries come from the
@@ -247,10 +313,20 @@ def main():
         n_postings = int(post_off_like[-1])
     else:
         post_off_like, n_postings = corpus.post_off, int(corpus.n_postings)
-    # weak scaling: rank r runs its own batch (different query seed per rank) against its replica
-    q_off, q_terms = m.synth_queries(wl["seed"] + 1000 + 7919 * rank, wl["queries"], wl["vocab"], wl["tmin"],
-                                     wl["tmax"], post_off_like, wl["zipf"])
-    nq = wl["queries"]
+    strong = wl.get("scaling") == "strong"
+    q_all = None
+    if strong:
+        # strong scaling: ONE batch (same seed on every rank), rank r answers its contiguous shard
+        from vectorchord_bm25_b200 import shard
+        q_all = m.synth_queries(wl["seed"] + 1000, wl["queries"], wl["vocab"], wl["tmin"], wl["tmax"], post_off_like,
+                                wl["zipf"])
+        q_off, q_terms, _lo, _hi = shard.shard_queries(q_all[0], q_all[1], rank, world)
+        nq, nq_job = _hi - _lo, wl["queries"]
+    else:
+        # weak scaling: rank r runs its own batch (different query seed per rank) against its replica
+        q_off, q_terms = m.synth_queries(wl["seed"] + 1000 + 7919 * rank, wl["queries"], wl["vocab"], wl["tmin"],
+                                         wl["tmax"], post_off_like, wl["zipf"])
+        nq, nq_job = wl["queries"], world * wl["queries"]
     config = {"workload": wl["desc"], "n_docs": wl["docs"], "vocab": wl["vocab"], "doc_len": wl["doclen"],
               "queries_per_gpu_per_step": nq, "terms_per_query": [wl["tmin"], wl["tmax"]], "k": k,
               "zipf_s": wl["zipf"], "postings": n_postings,
@@ -345,6 +421,17 @@ def main():
         top100 = {"value": nq / (ms100 / 1e3), "unit": "queries/s", "ms_per_step": ms100, "k": 100}
         b100.close()
 
+    # ---- strong scaling, gather to rank 0's host inside the clock (collective: every rank takes part) ----
+    strong_obj = None
+    if strong:
+        strong_obj = strong_leg(m, torch, dist, index, stream, q_all[0], q_all[1], k, rank, world, local_rank)
+    elif a.workload == "c3" and not a.no_strong:
+        qs = m.synth_queries(0xB25C0DE0 + 5 + 1000, STRONG_MIX_QUERIES, wl["vocab"], 1, 8, post_off_like, 0.0)
+        strong_obj = strong_leg(m, torch, dist, index, stream, qs[0], qs[1], k, rank, world, local_rank)
+        if strong_obj:
+            strong_obj["workload"] = (f"C5's query mix (1-8 terms, seed of configs[4]) on THIS corpus ({wl['docs']} docs): "
+                                      f"one batch of {STRONG_MIX_QUERIES} queries; the 50M-doc corpus itself: --workload c5")
+
     t = torch.tensor([ms_total, 1e3 * e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -354,8 +441,8 @@ def main():
             dist.destroy_process_group()
         return
     ms_step = ms_total / a.steps
-    value = world * nq / (ms_step / 1e3)
-    e2e_value = world * nq * e2e_steps / (e2e_ms / 1e3)
+    value = nq_job / (ms_step / 1e3)
+    e2e_value = nq_job * e2e_steps / (e2e_ms / 1e3)
     peak, peak_src = hbm_peak()
     kms = statistics.mean(kernel_ms_samples)
     # algorithmic bytes: 8 B per posting touched + 8 B per result slot + 16 B per query term.  With pruning
@@ -367,7 +454,7 @@ def main():
     h2d = 4 * (len(q_off) + len(q_terms) + nq)       # class-grouped ids + offsets + terms
     d2h = nq * k * 8 + nq * 4
     line = {"metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
             "dtype": "f32 filter + f64 exact re-score (u32 doc ids)", "data": "synthetic", "config": config,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None if a.no_prune else measured_traffic(a.workload, nq, k), "peak_source": peak_src, "kernel": kernel_name(wl["tmax"], k),
@@ -379,8 +466,12 @@ def main():
             "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / e2e_steps, "note": "bm25x_search_batch: host q_off/q_terms in, "
                     "host doc ids + f32 scores + counts out (page-locked host buffers)"},
-            "top100": top100, "gpu_launches": int(st.launches) * a.steps, "clocks": clocks,
+            "top100": top100, "strong_scaling": strong_obj, "gpu_launches": int(st.launches) * a.steps, "clocks": clocks,
             "index": {"device_bytes": int(info.device_bytes), "blocks": int(info.n_blocks), "avgdl": info.avgdl}}
+    if strong:   # the job's end-to-end number is the sharded batch WITH the gather to rank 0's host
+        line["e2e"] = {"value": strong_obj["value"], "unit": "queries/s", "h2d_bytes_per_step": strong_obj["h2d_bytes"],
+                       "d2h_bytes_per_step": strong_obj["d2h_bytes"], "ms_per_step": strong_obj["ms"],
+                       "note": strong_obj["note"], "per_rank_search_batch_qps": e2e_value}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

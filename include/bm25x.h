@@ -175,6 +175,10 @@ int bm25x_batch_prepare(bm25x_index *idx, uint32_t nq, const uint32_t *q_off, co
 int bm25x_batch_run(bm25x_batch *batch, void *stream, bm25x_search_stats *stats);
 int bm25x_batch_fetch(bm25x_batch *batch, uint32_t *out_doc, float *out_score, double *out_score64,
                       uint16_t *out_payload, uint32_t *out_n);
+/* Device addresses of the batch's result rows ([nq*k] u32 / f32 / f64 / u16[3], [nq] u32; any pointer may be NULL),
+ * written by bm25x_batch_run on its stream and valid until bm25x_batch_destroy — for callers that move results
+ * GPU → GPU (the NCCL gather of sharded results to one rank, vectorchord-bm25_b200/shard.py) instead of fetching. */
+int bm25x_batch_device_results(bm25x_batch *batch, void **doc, void **score, void **score64, void **payload, void **n);
 void bm25x_batch_destroy(bm25x_batch *batch);
 
 /* ---- the growing segment: documents inserted since the last seal.  bm25::search scans them one by one

@@ -29,10 +29,21 @@ def _worker(rank, world, port, out_path):
         return {"doc": d, "score": s, "n": n}
 
     got = shard.search_sharded(search_fn, q_off, q_terms, 10, rank, world)
+    # the tensor path of the GPU bench (bench.py strong_leg): this rank's rows as byte tensors, ONE dist.gather per
+    # array with the shards padded to a common size (37 = 19 + 18 rows), trimmed on rank 0
+    import torch
+    sub_off, sub_terms, lo, hi = shard.shard_queries(q_off, q_terms, rank, world)
+    part = search_fn(sub_off, sub_terms, 10)
+    as_bytes = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(hi - lo, -1))
+    rows = shard.gather_rows({k: as_bytes(part[k]) for k in ("doc", "score", "n")}, 37, rank, world)
     if rank == 0:
         want = search_fn(q_off, q_terms, 10)
         ok = all(np.array_equal(got[k], want[k]) for k in ("doc", "score", "n")) and got["doc"].shape == (37, 10)
+        for k in ("doc", "score", "n"):
+            ok = ok and rows[k].numpy().tobytes() == np.ascontiguousarray(want[k]).tobytes()
         open(out_path, "w").write("ok" if ok else "mismatch")
+    else:
+        assert rows is None
     dist.barrier()
     dist.destroy_process_group()
 

@@ -119,6 +119,7 @@ def load_library():
     L.bm25x_batch_prepare.argtypes = [vp, C.c_uint32, u32p, u32p, C.c_uint32, u8p, C.POINTER(vp)]
     L.bm25x_batch_run.argtypes = [vp, vp, C.POINTER(SearchStats)]
     L.bm25x_batch_fetch.argtypes = [vp, u32p, f32p, f64p, u16p, u32p]
+    L.bm25x_batch_device_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.bm25x_batch_destroy.argtypes = [vp]
     L.bm25x_batch_destroy.restype = None
     L.bm25x_evaluate_batch.argtypes = [vp, C.c_uint32, u32p, u32p, u32p, u32p, u32p, f64p]
@@ -509,6 +510,15 @@ class Batch:
                                                 _p(out["score64"], C.c_double), _p(out["payload"], C.c_uint16),
                                                 _p(out["n"], C.c_uint32)))
         return out
+
+    def device_results(self):
+        """Raw device addresses of the result rows: {"doc": (ptr, nbytes), "score": ..., "score64": ..., "n": ...}
+        (bm25x_batch_device_results) — for GPU → GPU transport of sharded results (shard.py)."""
+        p = [C.c_void_p() for _ in range(5)]
+        _check(load_library().bm25x_batch_device_results(self.h, *[C.byref(x) for x in p]))
+        slots = self.nq * self.k
+        return {"doc": (p[0].value, 4 * slots), "score": (p[1].value, 4 * slots), "score64": (p[2].value, 8 * slots),
+                "payload": (p[3].value, 6 * slots), "n": (p[4].value, 4 * self.nq)}
 
     def close(self):
         if getattr(self, "h", None):

@@ -419,6 +419,7 @@ extern "C" int bm25x_batch_run(bm25x_batch *b, void *stream_v, bm25x_search_stat
         sp.df = d.df;
         sp.blk_off = d.blk_off;
         sp.blk = d.blk;
+        sp.blk_ub = d.blk_ub;
         sp.s0f = d.s0f;
         sp.s0d = d.s0d;
         sp.s1d = d.s1d;
@@ -500,6 +501,20 @@ extern "C" int bm25x_batch_fetch(bm25x_batch *b, uint32_t *out_doc, float *out_s
     if (out_payload) BM25X_CUDA_TRY(cudaMemcpyAsync(out_payload, b->d_out_payload, 6 * slots, cudaMemcpyDeviceToHost, st));
     if (out_n) BM25X_CUDA_TRY(cudaMemcpyAsync(out_n, b->d_out_n, 4 * (size_t)b->nq, cudaMemcpyDeviceToHost, st));
     BM25X_CUDA_TRY(cudaStreamSynchronize(st));
+    return BM25X_OK;
+}
+
+extern "C" int bm25x_batch_device_results(bm25x_batch *b, void **doc, void **score, void **score64, void **payload,
+                                          void **n) {
+    if (!b) {
+        bm25x_set_error("bm25x_batch_device_results: null batch");
+        return BM25X_ERR_INVALID;
+    }
+    if (doc) *doc = b->d_out_doc;
+    if (score) *score = b->d_out_score;
+    if (score64) *score64 = b->d_out_score64;
+    if (payload) *payload = b->d_out_payload;
+    if (n) *n = b->d_out_n;
     return BM25X_OK;
 }
 

@@ -34,6 +34,7 @@ struct SearchParams {
     const uint32_t *df;
     const uint64_t *blk_off;
     const uint2 *blk;
+    const float *blk_ub;                // [n_blocks] per-block score bound (SummaryTuple.wand_*)
     const float *s0f;
     const double *s0d;
     const double *s1d;

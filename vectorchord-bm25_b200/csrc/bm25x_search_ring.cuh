@@ -54,6 +54,9 @@ namespace {
 #ifndef BM25X_RING_DENSE_T
 #define BM25X_RING_DENSE_T 48
 #endif
+#ifndef BM25X_PRUNE_ALPHA
+#define BM25X_PRUNE_ALPHA 0.5  // terms leave the streamed set while the sum of their score bounds stays <= ALPHA · k-th score
+#endif
 
 template <int M_, int KP_>
 struct RCfg {
@@ -107,6 +110,39 @@ __device__ __forceinline__ uint32_t ring_find(const Posting *rg, uint32_t a, uin
     const uint32_t l = ring_lower_bound<C>(rg, a, e, doc);
     if (l < e) {
         const Posting v = rg[l & C::RM];
+        if (v.doc == doc) return v.w;
+    }
+    return 0u;
+}
+
+// ---- probes of a term that is not streamed any more (candidates only; replaces Cursor::seek_block / seek of the
+// reference's parked cursors, search.rs:412-466): block table first (SummaryTuple.{min,max}_document_id), then inside
+// the 128-posting block.  `steps` counts the table entries / postings read (pruning statistics).
+// Returns l = 1 + index of the last block whose first document is <= doc (0: doc lies before the first block).
+__device__ __forceinline__ uint32_t probe_block(const SearchParams &p, uint64_t bbase, uint32_t nb, uint32_t doc,
+                                                uint32_t &steps) {
+    uint32_t l = 0, r = nb;
+    while (l < r) {
+        const uint32_t mid = (l + r) >> 1;
+        if (__ldg(&p.blk[bbase + mid].x) <= doc) l = mid + 1;
+        else r = mid;
+        steps++;
+    }
+    return l;
+}
+__device__ __forceinline__ uint32_t probe_in_block(const SearchParams &p, uint64_t pbase, uint32_t dfj, uint32_t block,
+                                                   uint32_t doc, uint32_t &steps) {
+    const uint32_t s = block * BM25X_BLOCK, e = min(s + BM25X_BLOCK, dfj);
+    const Posting *pp = p.post + pbase;
+    uint32_t l = s, r = e;
+    while (l < r) {
+        const uint32_t mid = (l + r) >> 1;
+        if (__ldg(&pp[mid].doc) < doc) l = mid + 1;
+        else r = mid;
+        steps++;
+    }
+    if (l < e) {
+        const Posting v = pp[l];
         if (v.doc == doc) return v.w;
     }
     return 0u;
@@ -172,6 +208,11 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
         // MaxScore pruning (warp-uniform): terms in ne_mask are no longer streamed; ub_ne = Σ of their score bounds
         uint32_t ne_mask = 0u;
         double ub_ne = 0.0;
+        uint32_t ne_list = 0u;     // the pruned terms in the order they left (ascending bound), 4 bits each (classes <= 8 terms)
+        int n_ne = 0;
+        float ne_prefix_f = 0.f;   // lane t: Σ bounds of the terms pruned before the t-th one, rounded up
+        float FloT = -1.f;         // filter threshold on the score over ALL terms (f.Flo: over the streamed terms only)
+        uint32_t probe_steps = 0;
         bool thr_new = false;     // the threshold moved since the pruned set was last reconsidered
         unsigned long long fetched = 0;
         // per-query pool / threshold state (warp-uniform registers)
@@ -192,6 +233,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
             f.tie_dk = (f.tie_sig != SIG_NONE && ne_mask == 0u) ? f.dk : INF;  // pruned terms: no tie shortcut
             const double flo = f.Sk * (1.0 - kEps) - ub_ne;
             f.Flo = __double2float_rd(flo);
+            FloT = __double2float_rd(f.Sk * (1.0 - kEps));
             // F = s0·tf/(tf+s1) >= flo  ⇔  tf >= flo/(s0-flo)·s1  (s0 > flo), never when s0 <= flo.  Solved in f64
             // from the exact s0, shrunk by 2^-20 to stay conservative in f32.
             f.ctf = __int_as_float(0x7f800000);  // +inf
@@ -256,9 +298,12 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                 mbar_wait(bar, parity);
                 parity ^= 1u;
             }
-            // MaxScore: move the terms with the smallest score bounds out of the streamed set while the sum of their
-            // bounds stays below 5 % of the k-th score (a document holding only such terms cannot enter; for the
-            // others the bound is added back in the filter and the exact contribution is probed at verification).
+            // MaxScore (the reference's WAND pivot rule, search.rs:152-169, applied to whole terms): the terms with the
+            // smallest score bounds leave the streamed set while the sum of their bounds stays <= ALPHA · k-th score.  A
+            // document holding only such terms cannot enter; for the others the bound is added back in the filter and
+            // the exact contributions are probed at verification — best bound first, giving up on a document as soon as
+            // the block-level bound (SummaryTuple.wand_*, search.rs:193-203) of the probed term plus the bounds of the
+            // terms still to probe cannot lift it over the threshold.
             // Only at chunk boundaries: inside a chunk the "last holder emits" rule relies on a fixed streamed set.
             if (p.prune && thr_new) {
                 thr_new = false;
@@ -275,8 +320,14 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                     const uint32_t ness = __popc(__ballot_sync(FULL, ess));
                     if (who == 0u || ness <= 1u) break;
                     const double ub = __longlong_as_double((long long)key);
-                    if (!(ub_ne + ub <= 0.05 * f.Sk)) break;
-                    ne_mask |= 1u << (__ffs(who) - 1);
+                    if (!(ub_ne + ub <= (double)BM25X_PRUNE_ALPHA * f.Sk)) break;
+                    const int who_i = __ffs(who) - 1;
+                    if (C::M <= 8) {
+                        ne_list |= (uint32_t)who_i << (4 * n_ne);
+                        if (lane == n_ne) ne_prefix_f = __double2float_ru(ub_ne);
+                    }
+                    n_ne++;
+                    ne_mask |= 1u << who_i;
                     ub_ne += ub;
                     changed = true;
                 }
@@ -380,7 +431,8 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                                 const uint32_t nbq = __shfl_sync(FULL, nbj, i), dfq = __shfl_sync(FULL, dfj, i);
                                 wi = 0u;
                                 if (keep) {
-                                    wi = probe_global(p, pb, bb, nbq, dfq, doc);
+                                    const uint32_t l = probe_block(p, bb, nbq, doc, probe_steps);
+                                    if (l > 0u) wi = probe_in_block(p, pb, dfq, l - 1u, doc, probe_steps);
                                     if (wi) sig = make_sig(i, wi);
                                 }
                             }
@@ -390,9 +442,48 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                             }
                         };
                         if constexpr (KEEPW) {
+                            if (ne_mask) {
+                                // pruned terms: probe in HBM, largest bound first; Fres = f32 score over the holders
+                                // found so far, rest = Σ bounds of the pruned terms not probed yet
+                                float Fres = F;
+                                for (int t = n_ne - 1; t >= 0; --t) {
+                                    const int i = (int)((ne_list >> (4 * t)) & 15u);
+                                    const uint64_t pb = __shfl_sync(FULL, pbase, i), bb = __shfl_sync(FULL, bbase, i);
+                                    const uint32_t nbq = __shfl_sync(FULL, nbj, i), dfq = __shfl_sync(FULL, dfj, i);
+                                    const float s0 = __shfl_sync(FULL, s0f, i);
+                                    const float rest = __shfl_sync(FULL, ne_prefix_f, t);
+                                    uint32_t wi = 0u;
+                                    if (keep) {
+                                        const uint32_t l = probe_block(p, bb, nbq, doc, probe_steps);
+                                        bool inside = false;
+                                        if (l > 0u && __ldg(&p.blk[bb + l - 1u].y) >= doc) {
+                                            // block-max test before the deep seek (search.rs:193-203)
+                                            if (Fres + __ldg(&p.blk_ub[bb + l - 1u]) + rest < FloT) keep = false;
+                                            else inside = true;
+                                        }
+                                        if (inside) wi = probe_in_block(p, pb, dfq, l - 1u, doc, probe_steps);
+                                        if (wi) {
+                                            Fres += score_f32(wi, s0, s1f);
+                                            sig = make_sig(i, wi);
+                                        }
+                                        if (keep && Fres + rest < FloT) keep = false;
+                                    }
 #pragma unroll
-                            for (int i = 0; i < C::M; ++i)
-                                if (i < (int)m) exact_term(i, wv[i]);
+                                    for (int ii = 0; ii < C::M; ++ii)
+                                        if (ii == i) wv[ii] = wi;
+                                }
+                            }
+                            if (__any_sync(FULL, keep)) {
+#pragma unroll
+                                for (int i = 0; i < C::M; ++i)
+                                    if (i < (int)m) {
+                                        const double s0 = __shfl_sync(FULL, s0d, i);
+                                        if (keep && wv[i]) {
+                                            Sx = __dadd_rn(Sx, score_f64(wv[i], s0, p.s1d));
+                                            cnt_all++;
+                                        }
+                                    }
+                            }
                         } else {
 #pragma unroll 1
                             for (int i = 0; i < (int)m; ++i) {
@@ -559,6 +650,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
         }
         if (lane == 0) p.out_n[qid] = (uint32_t)pn;
         if (p.fetched) {
+            fetched += probe_steps;  // block-table entries / postings read by the probes of pruned terms
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) fetched += __shfl_xor_sync(FULL, fetched, o);
             if (lane == 0) atomicAdd(p.fetched, fetched);

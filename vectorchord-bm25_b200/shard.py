@@ -62,6 +62,32 @@ def shard_queries(q_off, q_terms, rank: int, world: int):
     return sub_off, np.asarray(q_terms, dtype=np.uint32)[q_off[lo]:q_off[hi]], lo, hi
 
 
+def gather_rows(parts: dict, n_total: int, rank: int, world: int, dst: int = 0):
+    """Collective.  parts: {name: torch tensor [n_local, ...]} holding this rank's rows of a contiguous row sharding
+    (shard_bounds) — CUDA tensors under NCCL (the rows travel GPU → GPU over NVLink), CPU tensors under gloo.
+    Returns {name: tensor [n_total, ...]} on `dst` (same device as the inputs), None elsewhere.  Shards differ by at
+    most one row: every rank contributes max-shard rows (one padded row at most) to ONE dist.gather per array."""
+    import torch
+    import torch.distributed as dist
+
+    sizes = [shard_bounds(n_total, r, world)[1] - shard_bounds(n_total, r, world)[0] for r in range(world)]
+    mx = max(sizes) if sizes else 0
+    out = {}
+    for name, t in parts.items():
+        if t.shape[0] != mx:   # pad to the common shard size
+            pad = torch.zeros((mx - t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+            t = torch.cat([t, pad], dim=0)
+        t = t.contiguous()
+        if world == 1:
+            out[name] = t[:n_total]
+            continue
+        bufs = [torch.empty_like(t) for _ in range(world)] if rank == dst else None
+        dist.gather(t, bufs, dst=dst)
+        if rank == dst:
+            out[name] = torch.cat([b[:sizes[r]] for r, b in enumerate(bufs)], dim=0)
+    return out if rank == dst else None
+
+
 def search_sharded(search_fn, q_off, q_terms, k: int, rank: int, world: int, dst: int = 0):
     """Collective. search_fn(q_off, q_terms, k) -> {"doc": [n,k], "score": [n,k], "n": [n], ...} on this rank's shard.
     Returns the concatenated result (query order preserved) on rank `dst`, None elsewhere."""
