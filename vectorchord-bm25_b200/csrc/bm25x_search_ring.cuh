@@ -70,7 +70,8 @@ struct RCfg {
     static constexpr uint32_t ACC_DOCS = (1u << LOG_S) / 4u;
     static constexpr int U = BM25X_RING_U;          // 16-byte shared loads (2 postings) per lane and trip
     static constexpr int TRIP = 64 * U;             // postings per warp trip
-    static constexpr int LCAP = TRIP + 64;          // candidate list entries (verified when > 64 are listed)
+    static constexpr int TMAX = 32 / (2 * U) < 2 ? 32 / (2 * U) : 2;  // trips between two compactions of the detected postings
+    static constexpr int LCAP = TMAX * TRIP + 64;   // candidate list entries (verified when > 64 are listed)
     static constexpr int INIT = BM25X_RING_INIT;    // postings per run in the very first load (a threshold exists early)
     static constexpr size_t off_ring = 0;
     static constexpr size_t off_map = off_ring + (size_t)M_ * R * sizeof(Posting);
@@ -529,10 +530,15 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                     const uint4 *rg = (const uint4 *)(rings + (size_t)j * C::R);
                     const uint32_t tdk = f.tie_dk;  // snapshot with tw: a stale (looser) pair stays valid, thresholds only tighten
                     uint32_t pb = a & ~1u;
-                    // trips of TRIP postings until the run is done or the candidate list wants to be verified
-                    auto run = [&](auto test_c, auto mark_c) {
+                    // Up to TMAX trips of TRIP postings, then ONE compaction of the detected postings (a bit per posting
+                    // slot in `hm`; the per-trip ballot compaction cost as much as the test itself).
+                    auto run = [&](auto test_c, auto mark_c, auto solo_c) {
                         constexpr bool TEST = decltype(test_c)::value, MARK = decltype(mark_c)::value;
-                        for (; pb < ee && nc <= 64u; pb += C::TRIP) {
+                        constexpr bool SOLO = decltype(solo_c)::value;
+                        const uint32_t pb0 = pb;
+                        uint32_t hm = 0u;
+#pragma unroll 1
+                        for (int t = 0; t < C::TMAX && pb < ee; ++t, pb += C::TRIP) {
                             uint4 q[C::U];
                             uint32_t ix[C::U];
 #pragma unroll
@@ -540,48 +546,60 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                                 ix[u] = pb + 2u * (uint32_t)(lane + 32 * u);
                                 q[u] = rg[(ix[u] >> 1) & (C::RM >> 1)];
                             }
-                            bool c[2 * C::U];
-                            bool anyc = false;
+                            uint32_t bits = 0u;
 #pragma unroll
                             for (int u = 0; u < C::U; ++u) {
 #pragma unroll
                                 for (int h = 0; h < 2; ++h) {
                                     const uint32_t doc = h ? q[u].z : q[u].x, w = h ? q[u].w : q[u].y;
                                     const bool valid = ix[u] + h - a < nj;  // unsigned: also false below a
-                                    bool hit = false;
+                                    bool c = false;
                                     if (TEST || MARK) {
                                         const uint32_t slot = ring_slot(doc, C::LOG_S);
-                                        if (TEST) hit = map[slot] == genv;
+                                        if (TEST) c = map[slot] == genv;
                                         if (MARK && valid) map[slot] = (uint8_t)genv;
                                     }
-                                    const bool solo = w > wl && !(w == tw && doc > tdk);
-                                    c[2 * u + h] = valid && (hit || solo);
-                                    anyc |= c[2 * u + h];
+                                    if (SOLO) c = c || (w > wl && !(w == tw && doc > tdk));
+                                    if (valid && c) bits |= 1u << (2 * u + h);
                                 }
                             }
-                            if (__any_sync(FULL, anyc)) {
+                            hm |= bits << (2 * C::U * t);
+                        }
+                        if (__any_sync(FULL, hm != 0u)) {
+                            const uint32_t cnt = __popc(hm);
+                            uint32_t incl = cnt;
 #pragma unroll
-                                for (int u = 0; u < C::U; ++u) {
-#pragma unroll
-                                    for (int h = 0; h < 2; ++h) {
-                                        const uint32_t mc = __ballot_sync(FULL, c[2 * u + h]);
-                                        if (c[2 * u + h])
-                                            cand[nc + __popc(mc & lt_mask)] = ((uint32_t)j << 16) | ((ix[u] + h) & C::RM);
-                                        nc += __popc(mc);
-                                    }
-                                }
-                                __syncwarp();
+                            for (int o = 1; o < 32; o <<= 1) {
+                                const uint32_t v = __shfl_up_sync(FULL, incl, o);
+                                if (lane >= o) incl += v;
                             }
+                            uint32_t pos = nc + incl - cnt;
+                            for (uint32_t mm = hm; mm; mm &= mm - 1u) {
+                                const uint32_t bpos = (uint32_t)__ffs(mm) - 1u;
+                                const uint32_t t = bpos / (2 * C::U), sl = bpos % (2 * C::U);
+                                const uint32_t idx = pb0 + t * C::TRIP + 2u * (uint32_t)(lane + 32 * (sl >> 1)) + (sl & 1u);
+                                cand[pos++] = ((uint32_t)j << 16) | (idx & C::RM);
+                            }
+                            nc += __shfl_sync(FULL, incl, 31);
+                            __syncwarp();
                         }
                     };
                     const bool mark = multi && todo != 0u, test = multi && !first;
+                    const bool solo = wl != 0xFFFFFFFFu;  // no single-term posting of this run can pass: skip the test
                     for (;;) {
-                        if (test && mark) run(std::true_type(), std::true_type());
-                        else if (mark) run(std::false_type(), std::true_type());
-                        else if (test) run(std::true_type(), std::false_type());
-                        else run(std::false_type(), std::false_type());
+                        if (solo) {
+                            if (test && mark) run(std::true_type(), std::true_type(), std::true_type());
+                            else if (mark) run(std::false_type(), std::true_type(), std::true_type());
+                            else if (test) run(std::true_type(), std::false_type(), std::true_type());
+                            else run(std::false_type(), std::false_type(), std::true_type());
+                        } else {
+                            if (test && mark) run(std::true_type(), std::true_type(), std::false_type());
+                            else if (mark) run(std::false_type(), std::true_type(), std::false_type());
+                            else if (test) run(std::true_type(), std::false_type(), std::false_type());
+                            else pb = ee;  // nothing to learn from this run in this window
+                        }
+                        if (nc > 64u) verify();
                         if (pb >= ee) break;
-                        verify();  // the list is full: settle it, then resume this run
                     }
                     first = false;
                     __syncwarp();  // this run's marks are visible to the next run's tests
