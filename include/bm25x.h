@@ -29,7 +29,7 @@ extern "C" {
 #define BM25X_ERR_UNSUPPORTED 4 /* k > BM25X_MAX_K, > BM25X_MAX_QUERY_TERMS live terms, tf >= 2^24 */
 #define BM25X_ERR_LIMIT_ZERO 5  /* k == 0: "number of needed rows is set to 0" (scanners/default.rs:114-116) */
 
-#define BM25X_MAX_K 1024
+#define BM25X_MAX_K 65535 /* the reference's bm25.limit maximum (src/index/gucs.rs:37-46) */
 #define BM25X_MAX_QUERY_TERMS 32
 #define BM25X_TERM_MISSING 0xFFFFFFFFu
 #define BM25X_KEY_WIDTH 16 /* crates/bm25/src/lib.rs:37 WIDTH */

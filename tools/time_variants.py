@@ -18,6 +18,8 @@ sys.path.insert(0, ROOT)
 WL = {  # name: (queries, tmin, tmax, k, zipf)
     "c3": (100_000, 3, 3, 10, 0.0), "c3k100": (100_000, 3, 3, 100, 0.0), "c5mix": (100_000, 1, 8, 10, 0.0),
     "c2": (100_000, 1, 1, 10, 0.0), "c3k1000": (20_000, 3, 3, 1000, 0.0),
+    # VAR_CORPUS=zipf (the C4 corpus: Zipf(1) term frequencies): 8-term queries, pruning on / off (exhaustive)
+    "c4": (4_000, 8, 8, 10, 1.0), "c4np": (400, 8, 8, 10, 1.0), "c4mix": (20_000, 1, 8, 10, 1.0),
 }
 
 
@@ -26,12 +28,16 @@ def one(docs, workloads):
     import _pkg
     m = _pkg.load()
     t0 = time.time()
-    c = m.synth_corpus(0xB25C0DE0 + 3, docs, 100_000, 128, 128, 0.0)
+    zipf_corpus = os.environ.get("VAR_CORPUS", "uniform") == "zipf"
+    c = m.synth_corpus(0xB25C0DE0 + (4 if zipf_corpus else 3), docs, 100_000, 128, 128, 1.0 if zipf_corpus else 0.0)
     ix = m.Index.from_corpus(c)
     out = {"build_s": round(time.time() - t0, 1)}
     for name in workloads:
         nq, tmin, tmax, k, zipf = WL[name]
-        q_off, q_terms = m.synth_queries(0xB25C0DE0 + 1003, nq, 100_000, tmin, tmax, c.post_off, zipf)
+        assert (zipf > 0) == zipf_corpus, "workload and VAR_CORPUS do not match"
+        q_off, q_terms = m.synth_queries(0xB25C0DE0 + 1003 + (1 if zipf_corpus else 0), nq, 100_000, tmin, tmax,
+                                         c.post_off, zipf)
+        ix.set_option("prune", 0 if name.endswith("np") else 1)
         b = ix.prepare(q_off, q_terms, k)
         for _ in range(3):
             b.run()

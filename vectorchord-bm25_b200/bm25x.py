@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # BM25X_LIBRARY: load another build of the same library (tools/time_variants.py times tuning variants side by side)
 _SO = os.environ.get("BM25X_LIBRARY") or os.path.join(_HERE, "libbm25x.so")
 
-MAX_K = 1024
+MAX_K = 65535
 MAX_QUERY_TERMS = 32
 TERM_MISSING = 0xFFFFFFFF
 

@@ -132,11 +132,13 @@ static int launch_class(const bm25x_index *ix, SearchParams &sp, cudaStream_t st
 int bm25x_launch_ring_kp64(int device, int sm_count, const SearchParams &sp, int M, cudaStream_t stream);
 int bm25x_launch_ring_kp256(int device, int sm_count, const SearchParams &sp, int M, cudaStream_t stream);
 int bm25x_launch_ring_kp2048(int device, int sm_count, const SearchParams &sp, int M, cudaStream_t stream);
+int bm25x_launch_ring_kp131072(int device, int sm_count, const SearchParams &sp, int M, cudaStream_t stream);
 
 static int launch_ring_k(const bm25x_index *ix, const SearchParams &sp, int M, cudaStream_t stream) {
     if (sp.k <= 32) return bm25x_launch_ring_kp64(ix->device, ix->sm_count, sp, M, stream);
     if (sp.k <= 224) return bm25x_launch_ring_kp256(ix->device, ix->sm_count, sp, M, stream);
-    return bm25x_launch_ring_kp2048(ix->device, ix->sm_count, sp, M, stream);
+    if (sp.k <= 1024) return bm25x_launch_ring_kp2048(ix->device, ix->sm_count, sp, M, stream);
+    return bm25x_launch_ring_kp131072(ix->device, ix->sm_count, sp, M, stream);  // candidate pools in HBM
 }
 
 // kernel v5 (warp per query): k <= 128 and <= 8 live terms
@@ -219,7 +221,7 @@ extern "C" int bm25x_batch_prepare(bm25x_index *ix, uint32_t nq, const uint32_t 
         bm25x_set_error("number of needed rows is set to 0");  // scanners/default.rs:114-116
         return BM25X_ERR_LIMIT_ZERO;
     }
-    if (k > BM25X_MAX_K) {
+    if (k > BM25X_MAX_K || (k > 1024 && kernel_generation() != 6)) {
         bm25x_set_error("bm25x_batch_prepare: k=%u > BM25X_MAX_K=%d", k, BM25X_MAX_K);
         return BM25X_ERR_UNSUPPORTED;
     }

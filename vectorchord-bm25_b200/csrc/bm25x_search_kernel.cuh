@@ -42,6 +42,7 @@ struct SearchParams {
     const uint16_t *payload;
     const double *ubd;                  // per-term upper bound of one posting's exact score
     unsigned long long *fetched;        // Σ postings actually loaded into shared memory (pruning statistics)
+    uint8_t *pool_scratch;              // k > 1024: per-warp candidate pools in HBM (k_search_ring, RCfg::POOL_GLOBAL)
     int prune;
     float s1f_min;                      // min over the documents of s1f[fieldnorm]
     uint32_t n_docs;
@@ -167,8 +168,8 @@ struct Smem {
     static constexpr size_t off_ctrl = off_s1f + 256 * 4;
     static constexpr size_t total = off_ctrl + ((sizeof(Ctrl) + 15) & ~(size_t)15);
     static_assert((size_t)C::M * (C::T + 2) * 2 <= map_bytes, "cold-path bounds must fit in the tag maps");
-    static_assert(C::PC >= BM25X_MAX_K + C::QC && (C::PC & (C::PC - 1)) == 0, "pool: power of two >= k + one drain");
-    static_assert(C::PC >= BM25X_MAX_K + C::W * C::QCW, "pool must hold k + one chunk of hot-path candidates");
+    static_assert(C::PC >= 1024 + C::QC && (C::PC & (C::PC - 1)) == 0, "pool: power of two >= k + one drain");
+    static_assert(C::PC >= 1024 + C::W * C::QCW, "pool must hold k + one chunk of hot-path candidates");
     static_assert(C::STAGE_POSTINGS <= 65536, "stage positions are 16-bit");
 };
 

@@ -11,7 +11,7 @@
 namespace {
 
 template <class C>
-int launch_ring(int device, int sm_count, const SearchParams &sp, cudaStream_t stream) {
+int launch_ring(int device, int sm_count, const SearchParams &sp_in, cudaStream_t stream) {
     static bool configured[64] = {false};
     auto kern = k_search_ring<C>;
     if (!configured[device & 63]) {
@@ -19,10 +19,18 @@ int launch_ring(int device, int sm_count, const SearchParams &sp, cudaStream_t s
         configured[device & 63] = true;
     }
     uint32_t grid = (uint32_t)sm_count;  // persistent: one CTA per SM, every warp pulls queries from the work counter
-    const uint32_t need = (sp.nq + C::WARPS - 1) / C::WARPS;
+    const uint32_t need = (sp_in.nq + C::WARPS - 1) / C::WARPS;
     if (grid > need) grid = need;
+    SearchParams sp = sp_in;
+    sp.pool_scratch = nullptr;
+    if (C::POOL_GLOBAL) {  // stream-ordered scratch for the per-warp pools, released right behind the kernel
+        const size_t bytes = (size_t)grid * C::WARPS * (size_t)C::KP * 16;
+        BM25X_CUDA_TRY(cudaMallocAsync((void **)&sp.pool_scratch, bytes, stream));
+    }
     kern<<<grid, C::THREADS, C::total, stream>>>(sp);
-    BM25X_CUDA_TRY(cudaGetLastError());
+    cudaError_t e = cudaGetLastError();
+    if (sp.pool_scratch) cudaFreeAsync(sp.pool_scratch, stream);
+    BM25X_CUDA_TRY(e);
     return BM25X_OK;
 }
 

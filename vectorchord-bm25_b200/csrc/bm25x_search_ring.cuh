@@ -62,6 +62,10 @@ template <int M_, int KP_>
 struct RCfg {
     static constexpr int M = M_;    // max live terms (lanes 0..M-1 own the terms)
     static constexpr int KP = KP_;  // pool capacity (power of two >= k + 32)
+    // pools beyond 2048 entries (k > 1024, up to the reference's bm25.limit maximum of 65535, src/index/gucs.rs:37-46)
+    // live in HBM: one KP-entry slice of SearchParams::pool_scratch per warp
+    static constexpr bool POOL_GLOBAL = KP_ > 2048;
+    static constexpr size_t POOL_SMEM = POOL_GLOBAL ? 0 : (size_t)KP_;
     // ring postings per run: half a ring is in flight while the other half is processed
     static constexpr int LOG_R = BM25X_RING_LOG_R > 0 ? BM25X_RING_LOG_R : (M_ <= 4 ? 9 : (M_ <= 8 ? 8 : 7));
     static constexpr int R = 1 << LOG_R;
@@ -76,9 +80,9 @@ struct RCfg {
     static constexpr size_t off_ring = 0;
     static constexpr size_t off_map = off_ring + (size_t)M_ * R * sizeof(Posting);
     static constexpr size_t off_pool_s = off_map + ((size_t)1 << LOG_S);
-    static constexpr size_t off_pool_d = off_pool_s + (size_t)KP * 8;
-    static constexpr size_t off_pool_g = off_pool_d + (size_t)KP * 4;
-    static constexpr size_t off_cand = off_pool_g + (size_t)KP * 4;
+    static constexpr size_t off_pool_d = off_pool_s + POOL_SMEM * 8;
+    static constexpr size_t off_pool_g = off_pool_d + POOL_SMEM * 4;
+    static constexpr size_t off_cand = off_pool_g + POOL_SMEM * 4;
     static constexpr size_t off_bar = off_cand + (size_t)LCAP * 4;
     static constexpr size_t warp_bytes = (off_bar + 8 + 127) & ~(size_t)127;
     static constexpr size_t off_s1f = 0;  // CTA-shared: 1 KiB table first, then the warps
@@ -161,9 +165,16 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
     Posting *rings = (Posting *)(ws + C::off_ring);
     uint8_t *map = ws + C::off_map;
     WPool<C> pl;
-    pl.s = (uint64_t *)(ws + C::off_pool_s);
-    pl.d = (uint32_t *)(ws + C::off_pool_d);
-    pl.g = (uint32_t *)(ws + C::off_pool_g);
+    if (C::POOL_GLOBAL) {
+        uint8_t *slice = p.pool_scratch + ((size_t)blockIdx.x * C::WARPS + wid) * ((size_t)C::KP * 16);
+        pl.s = (uint64_t *)slice;
+        pl.d = (uint32_t *)(slice + (size_t)C::KP * 8);
+        pl.g = (uint32_t *)(slice + (size_t)C::KP * 12);
+    } else {
+        pl.s = (uint64_t *)(ws + C::off_pool_s);
+        pl.d = (uint32_t *)(ws + C::off_pool_d);
+        pl.g = (uint32_t *)(ws + C::off_pool_g);
+    }
     uint32_t *cand = (uint32_t *)(ws + C::off_cand);
     uint64_t *bar = (uint64_t *)(ws + C::off_bar);
     if (lane == 0) {
