@@ -74,8 +74,8 @@ struct RCfg {
     static constexpr uint32_t ACC_DOCS = (1u << LOG_S) / 4u;
     static constexpr int U = BM25X_RING_U;          // 16-byte shared loads (2 postings) per lane and trip
     static constexpr int TRIP = 64 * U;             // postings per warp trip
-    static constexpr int TMAX = 32 / (2 * U) < 2 ? 32 / (2 * U) : 2;  // trips between two compactions of the detected postings
-    static constexpr int LCAP = TMAX * TRIP + 64;   // candidate list entries (verified when > 64 are listed)
+    static constexpr int TMAX = 32 / (2 * U) < 4 ? 32 / (2 * U) : 4;  // trips between two compactions of the detected postings
+    static constexpr int LCAP = TMAX * TRIP + 64;   // candidate list entries, 16 bits each (verified when > 64 are listed)
     static constexpr int INIT = BM25X_RING_INIT;    // postings per run in the very first load (a threshold exists early)
     static constexpr size_t off_ring = 0;
     static constexpr size_t off_map = off_ring + (size_t)M_ * R * sizeof(Posting);
@@ -83,7 +83,7 @@ struct RCfg {
     static constexpr size_t off_pool_d = off_pool_s + POOL_SMEM * 8;
     static constexpr size_t off_pool_g = off_pool_d + POOL_SMEM * 4;
     static constexpr size_t off_cand = off_pool_g + POOL_SMEM * 4;
-    static constexpr size_t off_bar = off_cand + (size_t)LCAP * 4;
+    static constexpr size_t off_bar = (off_cand + (size_t)LCAP * 2 + 7) & ~(size_t)7;
     static constexpr size_t warp_bytes = (off_bar + 8 + 127) & ~(size_t)127;
     static constexpr size_t off_s1f = 0;  // CTA-shared: 1 KiB table first, then the warps
     static constexpr size_t shared_bytes = 1024;
@@ -92,22 +92,25 @@ struct RCfg {
     static constexpr size_t total = shared_bytes + warp_bytes * WARPS;
     static constexpr int THREADS = WARPS * 32;
     static_assert(WARPS >= 1, "one warp must fit");
-    static_assert(R <= 65536 && M_ <= 32, "entry format: 16-bit ring position, 5-bit run");
+    static_assert(R <= 1024 && M_ <= 32 && ((1u << LOG_S) / 4u) <= 32768u,
+                  "entry format: bit 15 = dense flavour (15-bit doc offset), else 5-bit run | 10-bit ring position");
     static_assert(ACC_DOCS >= 64, "accumulator too small");
 };
 
 __device__ __forceinline__ uint32_t ring_slot(uint32_t doc, int log_s) { return (doc * 0x9E3779B1u) >> (32 - log_s); }
 
-// lower_bound of `doc` in ring positions [a, e) (posting indices of the term; the ring holds index i at i & RM)
+// lower_bound of `doc` in ring positions [a, e) (posting indices of the term; the ring holds index i at i & RM).
+// Fixed LOG_R + 1 power-of-two steps, no data-dependent branch: every lane of a verification pass searches the same run,
+// and independent searches interleave (the while-loop form cost 135 warp instructions per search, profiles/r2b).
 template <class C>
 __device__ __forceinline__ uint32_t ring_lower_bound(const Posting *rg, uint32_t a, uint32_t e, uint32_t doc) {
-    uint32_t l = a, r = e;
-    while (l < r) {
-        const uint32_t mid = (l + r) >> 1;
-        if (rg[mid & C::RM].doc < doc) l = mid + 1;
-        else r = mid;
+    uint32_t pos = a;  // every posting before pos is < doc
+#pragma unroll
+    for (int s = C::LOG_R; s >= 0; --s) {
+        const uint32_t probe = pos + (1u << s);
+        if (probe <= e && rg[(probe - 1u) & C::RM].doc < doc) pos = probe;
     }
-    return l;
+    return pos;
 }
 // posting word of `doc` in [a, e), 0 when absent
 template <class C>
@@ -175,7 +178,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
         pl.d = (uint32_t *)(ws + C::off_pool_d);
         pl.g = (uint32_t *)(ws + C::off_pool_g);
     }
-    uint32_t *cand = (uint32_t *)(ws + C::off_cand);
+    uint16_t *cand = (uint16_t *)(ws + C::off_cand);
     uint64_t *bar = (uint64_t *)(ws + C::off_bar);
     if (lane == 0) {
         mbar_init(bar, 1);
@@ -259,6 +262,9 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                 tfmin = t < 16777216.f ? (t > 1.f ? (uint32_t)t : 1u) : 0x1000000u;
             }
             wlim = tfmin >= 0x1000000u ? 0xFFFFFFFFu : (tfmin << 8) - 1u;
+            // the term's best posting (its token-level bound) stays below the threshold: no posting of this run can
+            // enter alone, the hot loop drops the single-term test altogether
+            if (lane < (int)m && ubd < flo) wlim = 0xFFFFFFFFu;
             tiew = (f.tie_dk != INF && (f.tie_sig >> 27) == (uint32_t)lane) ? (f.tie_sig & 0x07FFFFFFu) : 0xFFFFFFFFu;
         };
         // cut the pool back to k and refresh the threshold (Results::push / threshold, search.rs:284-314)
@@ -389,13 +395,13 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                 for (uint32_t base = 0; base < nc; base += 32) {
                     const bool has = base + lane < nc;
                     const uint32_t ent = has ? cand[base + lane] : 0u;
-                    const bool by_doc = (ent >> 31) != 0u;            // dense flavour: document given as offset from lo
-                    const uint32_t j = by_doc ? 32u : (ent >> 16) & 31u;
+                    const bool by_doc = (ent >> 15) != 0u;            // dense flavour: document given as offset from lo
+                    const uint32_t j = by_doc ? 32u : (ent >> 10) & 31u;
                     Posting own;
                     own.doc = 0;
                     own.w = 0;
-                    if (has && !by_doc) own = rings[(size_t)j * C::R + (ent & 0xFFFFu)];
-                    const uint32_t doc = by_doc ? lo + (ent & 0x7FFFFFFFu) : own.doc;
+                    if (has && !by_doc) own = rings[(size_t)j * C::R + (ent & 0x3FFu)];
+                    const uint32_t doc = by_doc ? lo + (ent & 0x7FFFu) : own.doc;
                     float F = 0.f;
                     uint32_t cnt = 0, sig = SIG_NONE;
                     bool later = false;
@@ -524,130 +530,144 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                 nc = 0;
             };
 
+            // ---- candidate production (resumable) + ONE verification site ----
+            // sparse window: runs in ascending order; each run tests its documents against the marks of the earlier runs,
+            // then marks them.  dense window: scores summed in an f32 accumulator indexed by doc - lo (in the map's
+            // memory; docs are distinct inside a run: plain read-modify-write, __syncwarp between runs), then scanned.
+            uint32_t todo = 0u, ra = 0u, ree = 0u, rnj = 0u, wl = 0u, tw = 0u, tdk = 0u, pb = 0u, genv = 0u, dbase = 0u;
+            int rj = -1, variant = 0;
+            bool first = true, multi = false;
+            const uint4 *rg = nullptr;
             if (!dense) {
-                // ---- sparse window: runs in ascending order; test against the marks of the earlier runs, then mark ----
-                const uint32_t nonempty = __ballot_sync(FULL, act && e > rd);
-                const bool multi = C::M > 1 && __popc(nonempty) > 1;
+                todo = __ballot_sync(FULL, act && e > rd);
+                multi = C::M > 1 && __popc(todo) > 1;
                 if (multi) gen = gen % 255u + 1u;
-                const uint32_t genv = gen;
-                uint32_t todo = nonempty;
-                bool first = true;
-                while (todo) {
-                    const int j = __ffs(todo) - 1;
-                    todo &= todo - 1u;
-                    const uint32_t a = __shfl_sync(FULL, rd, j), ee = __shfl_sync(FULL, e, j);
-                    const uint32_t wl = __shfl_sync(FULL, wlim, j), tw = __shfl_sync(FULL, tiew, j);
-                    const uint32_t nj = ee - a;
-                    const uint4 *rg = (const uint4 *)(rings + (size_t)j * C::R);
-                    const uint32_t tdk = f.tie_dk;  // snapshot with tw: a stale (looser) pair stays valid, thresholds only tighten
-                    uint32_t pb = a & ~1u;
-                    // Up to TMAX trips of TRIP postings, then ONE compaction of the detected postings (a bit per posting
-                    // slot in `hm`; the per-trip ballot compaction cost as much as the test itself).
-                    auto run = [&](auto test_c, auto mark_c, auto solo_c) {
-                        constexpr bool TEST = decltype(test_c)::value, MARK = decltype(mark_c)::value;
-                        constexpr bool SOLO = decltype(solo_c)::value;
-                        const uint32_t pb0 = pb;
-                        uint32_t hm = 0u;
-#pragma unroll 1
-                        for (int t = 0; t < C::TMAX && pb < ee; ++t, pb += C::TRIP) {
-                            uint4 q[C::U];
-                            uint32_t ix[C::U];
-#pragma unroll
-                            for (int u = 0; u < C::U; ++u) {
-                                ix[u] = pb + 2u * (uint32_t)(lane + 32 * u);
-                                q[u] = rg[(ix[u] >> 1) & (C::RM >> 1)];
-                            }
-                            uint32_t bits = 0u;
-#pragma unroll
-                            for (int u = 0; u < C::U; ++u) {
-#pragma unroll
-                                for (int h = 0; h < 2; ++h) {
-                                    const uint32_t doc = h ? q[u].z : q[u].x, w = h ? q[u].w : q[u].y;
-                                    const bool valid = ix[u] + h - a < nj;  // unsigned: also false below a
-                                    bool c = false;
-                                    if (TEST || MARK) {
-                                        const uint32_t slot = ring_slot(doc, C::LOG_S);
-                                        if (TEST) c = map[slot] == genv;
-                                        if (MARK && valid) map[slot] = (uint8_t)genv;
-                                    }
-                                    if (SOLO) c = c || (w > wl && !(w == tw && doc > tdk));
-                                    if (valid && c) bits |= 1u << (2 * u + h);
-                                }
-                            }
-                            hm |= bits << (2 * C::U * t);
-                        }
-                        if (__any_sync(FULL, hm != 0u)) {
-                            const uint32_t cnt = __popc(hm);
-                            uint32_t incl = cnt;
-#pragma unroll
-                            for (int o = 1; o < 32; o <<= 1) {
-                                const uint32_t v = __shfl_up_sync(FULL, incl, o);
-                                if (lane >= o) incl += v;
-                            }
-                            uint32_t pos = nc + incl - cnt;
-                            for (uint32_t mm = hm; mm; mm &= mm - 1u) {
-                                const uint32_t bpos = (uint32_t)__ffs(mm) - 1u;
-                                const uint32_t t = bpos / (2 * C::U), sl = bpos % (2 * C::U);
-                                const uint32_t idx = pb0 + t * C::TRIP + 2u * (uint32_t)(lane + 32 * (sl >> 1)) + (sl & 1u);
-                                cand[pos++] = ((uint32_t)j << 16) | (idx & C::RM);
-                            }
-                            nc += __shfl_sync(FULL, incl, 31);
-                            __syncwarp();
-                        }
-                    };
-                    const bool mark = multi && todo != 0u, test = multi && !first;
-                    const bool solo = wl != 0xFFFFFFFFu;  // no single-term posting of this run can pass: skip the test
-                    for (;;) {
-                        if (solo) {
-                            if (test && mark) run(std::true_type(), std::true_type(), std::true_type());
-                            else if (mark) run(std::false_type(), std::true_type(), std::true_type());
-                            else if (test) run(std::true_type(), std::false_type(), std::true_type());
-                            else run(std::false_type(), std::false_type(), std::true_type());
-                        } else {
-                            if (test && mark) run(std::true_type(), std::true_type(), std::false_type());
-                            else if (mark) run(std::false_type(), std::true_type(), std::false_type());
-                            else if (test) run(std::true_type(), std::false_type(), std::false_type());
-                            else pb = ee;  // nothing to learn from this run in this window
-                        }
-                        if (nc > 64u) verify();
-                        if (pb >= ee) break;
-                    }
-                    first = false;
-                    __syncwarp();  // this run's marks are visible to the next run's tests
-                }
+                genv = gen;
             } else {
-                // ---- dense window: scores summed in an f32 accumulator indexed by doc - lo (in the map's memory;
-                // docs are distinct inside a run: plain read-modify-write, __syncwarp between runs) ----
                 float *acc = (float *)map;
                 for (uint32_t i = lane; i < (span + 3u) / 4u; i += 32) ((float4 *)acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                 __syncwarp();
-                uint32_t todo = __ballot_sync(FULL, act && e > rd);
-                while (todo) {
-                    const int j = __ffs(todo) - 1;
-                    todo &= todo - 1u;
+                uint32_t td = __ballot_sync(FULL, act && e > rd);
+                while (td) {
+                    const int j = __ffs(td) - 1;
+                    td &= td - 1u;
                     const uint32_t a = __shfl_sync(FULL, rd, j), ee = __shfl_sync(FULL, e, j);
                     const float s0 = __shfl_sync(FULL, s0f, j);
-                    const Posting *rg = rings + (size_t)j * C::R;
+                    const Posting *rgp = rings + (size_t)j * C::R;
                     for (uint32_t i = a + lane; i < ee; i += 32) {
-                        const Posting v = rg[i & C::RM];
+                        const Posting v = rgp[i & C::RM];
                         acc[v.doc - lo] += score_f32(v.w, s0, s1f);
                     }
                     __syncwarp();
                 }
-                for (uint32_t base = 0; base < span; base += 32) {
-                    const uint32_t o = base + lane;
-                    const float F = o < span ? acc[o] : 0.f;
-                    const bool c = F > 0.f && F >= f.Flo;
-                    const uint32_t mc = __ballot_sync(FULL, c);
-                    if (mc) {
-                        if (c) cand[nc + __popc(mc & lt_mask)] = 0x80000000u | o;
-                        nc += __popc(mc);
-                        __syncwarp();
-                        if (nc > 64u) verify();
-                    }
-                }
             }
-            if (nc) verify();
+            // Up to TMAX trips of TRIP postings of the current run, then ONE compaction of the detected postings (a bit
+            // per posting slot in `hm`: per-trip ballot compaction cost as much as the test itself).
+            auto run = [&](auto test_c, auto mark_c, auto solo_c) {
+                constexpr bool TEST = decltype(test_c)::value, MARK = decltype(mark_c)::value;
+                constexpr bool SOLO = decltype(solo_c)::value;
+                const uint32_t pb0 = pb;
+                uint32_t hm = 0u;
+#pragma unroll 1
+                for (int t = 0; t < C::TMAX && pb < ree; ++t, pb += C::TRIP) {
+                    uint4 q[C::U];
+                    uint32_t ix[C::U];
+#pragma unroll
+                    for (int u = 0; u < C::U; ++u) {
+                        ix[u] = pb + 2u * (uint32_t)(lane + 32 * u);
+                        q[u] = rg[(ix[u] >> 1) & (C::RM >> 1)];
+                    }
+                    uint32_t bits = 0u;
+                    auto body = [&](auto check_c) {
+                        constexpr bool CHECK = decltype(check_c)::value;  // trips at the ends of the range test validity
+#pragma unroll
+                        for (int u = 0; u < C::U; ++u) {
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                const uint32_t doc = h ? q[u].z : q[u].x, w = h ? q[u].w : q[u].y;
+                                const bool valid = !CHECK || ix[u] + h - ra < rnj;  // unsigned: also false below ra
+                                bool c = false;
+                                if (TEST || MARK) {
+                                    const uint32_t slot = ring_slot(doc, C::LOG_S);
+                                    if (TEST) c = map[slot] == genv;
+                                    if (MARK && valid) map[slot] = (uint8_t)genv;
+                                }
+                                if (SOLO) c = c | ((w > wl) & !((w == tw) & (doc > tdk)));  // bitwise: no branches
+                                bits |= (uint32_t)(valid & c) << (2 * u + h);
+                            }
+                        }
+                    };
+                    if (pb >= ra && pb + C::TRIP <= ree) body(std::false_type());
+                    else body(std::true_type());
+                    hm |= bits << (2 * C::U * t);
+                }
+                for (;;) {  // compaction: one listed posting per lane and round
+                    const uint32_t bal = __ballot_sync(FULL, hm != 0u);
+                    if (!bal) break;
+                    if (hm) {
+                        const uint32_t bpos = (uint32_t)__ffs(hm) - 1u;
+                        hm &= hm - 1u;
+                        const uint32_t t = bpos / (2 * C::U), sl = bpos % (2 * C::U);
+                        const uint32_t idx = pb0 + t * C::TRIP + 2u * (uint32_t)(lane + 32 * (sl >> 1)) + (sl & 1u);
+                        cand[nc + __popc(bal & lt_mask)] = (uint16_t)(((uint32_t)rj << 10) | (idx & C::RM));
+                    }
+                    nc += __popc(bal);
+                }
+            };
+            bool finished = false;
+            while (!finished) {
+                if (!dense) {
+                    if (pb >= ree) {  // next run
+                        if (rj >= 0) {
+                            first = false;
+                            __syncwarp();  // this run's marks are visible to the next run's tests
+                        }
+                        if (!todo) {
+                            finished = true;
+                        } else {
+                            rj = __ffs(todo) - 1;
+                            todo &= todo - 1u;
+                            ra = __shfl_sync(FULL, rd, rj);
+                            ree = __shfl_sync(FULL, e, rj);
+                            wl = __shfl_sync(FULL, wlim, rj);
+                            tw = __shfl_sync(FULL, tiew, rj);
+                            rnj = ree - ra;
+                            rg = (const uint4 *)(rings + (size_t)rj * C::R);
+                            tdk = f.tie_dk;  // snapshot with tw: a stale (looser) pair stays valid, thresholds only tighten
+                            pb = ra & ~1u;
+                            // wl == ~0: no single-term posting of this run can pass → the loop variant without the test
+                            variant = (wl != 0xFFFFFFFFu ? 4 : 0) | (multi && !first ? 2 : 0) | (multi && todo != 0u ? 1 : 0);
+                            if (variant == 0) pb = ree;  // nothing to learn from this run in this window
+                        }
+                    }
+                    if (!finished && pb < ree) {
+                        switch (variant) {
+                            case 1: run(std::false_type(), std::true_type(), std::false_type()); break;
+                            case 2: run(std::true_type(), std::false_type(), std::false_type()); break;
+                            case 3: run(std::true_type(), std::true_type(), std::false_type()); break;
+                            case 4: run(std::false_type(), std::false_type(), std::true_type()); break;
+                            case 5: run(std::false_type(), std::true_type(), std::true_type()); break;
+                            case 6: run(std::true_type(), std::false_type(), std::true_type()); break;
+                            default: run(std::true_type(), std::true_type(), std::true_type()); break;
+                        }
+                        __syncwarp();  // the listed entries are visible to every lane
+                    }
+                } else {
+                    const float *acc = (const float *)map;
+                    while (dbase < span && nc <= 64u) {
+                        const uint32_t o = dbase + lane;
+                        const float F = o < span ? acc[o] : 0.f;
+                        const bool c = F > 0.f && F >= f.Flo;
+                        const uint32_t mc = __ballot_sync(FULL, c);
+                        if (c) cand[nc + __popc(mc & lt_mask)] = (uint16_t)(0x8000u | o);
+                        nc += __popc(mc);
+                        dbase += 32;
+                    }
+                    __syncwarp();
+                    finished = dbase >= span;
+                }
+                if (nc > 64u || (finished && nc)) verify();
+            }
             rd = e;
             lo = hi;
             if (last) break;
