@@ -226,7 +226,6 @@ class OracleIndex:
             lib().orc_index_free(self.h)
             self.h = None
 
-    @property
     def block_wand(self):
         """(wand_fieldnorm u8[], wand_term_frequency u32[]) of every block, (token, block) order (flush.rs:101-120)."""
         n = int(lib().orc_index_n_blocks(self.h))
@@ -235,6 +234,7 @@ class OracleIndex:
         lib().orc_index_block_wand(self.h, _p(fn, C.c_uint8), _p(tf, C.c_uint32))
         return fn[:n], tf[:n]
 
+    @property
     def avgdl(self):
         return lib().orc_index_avgdl(self.h)
 

@@ -14,6 +14,9 @@
 #define BM25X_DOC_INF 0xFFFFFFFFu   // exhausted-cursor sentinel, as search.rs:484-496
 
 void bm25x_set_error(const char *fmt, ...);
+// Host threads this process may really use: the affinity mask capped by the cgroup CPU quota (omp_get_max_threads()
+// ignores the quota: 128 threads spinning on a dozen granted cores cost the batch canonicalisation tens of ms).
+int bm25x_host_threads(int cap);
 
 #define BM25X_CUDA_TRY(expr)                                                                   \
     do {                                                                                       \

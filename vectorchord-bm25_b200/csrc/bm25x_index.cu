@@ -8,6 +8,7 @@
 #include <omp.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -25,6 +26,34 @@ void bm25x_set_error(const char *fmt, ...) {
 }
 
 extern "C" const char *bm25x_last_error(void) { return g_err; }
+
+int bm25x_host_threads(int cap) {
+    static const int granted = [] {
+        int n = omp_get_num_procs();  // honours the affinity mask
+        FILE *f = fopen("/sys/fs/cgroup/cpu.max", "r");
+        if (f) {
+            char q[64];
+            long long per = 0;
+            if (fscanf(f, "%63s %lld", q, &per) == 2 && strcmp(q, "max") != 0 && per > 0) {
+                const long long quota = (atoll(q) + per / 2) / per;
+                if (quota >= 1 && quota < n) n = (int)quota;
+            }
+            fclose(f);
+        } else if ((f = fopen("/sys/fs/cgroup/cpu/cpu.cfs_quota_us", "r"))) {
+            long long quota = -1, per = 100000;
+            if (fscanf(f, "%lld", &quota) != 1) quota = -1;
+            fclose(f);
+            FILE *g = fopen("/sys/fs/cgroup/cpu/cpu.cfs_period_us", "r");
+            if (g) {
+                if (fscanf(g, "%lld", &per) != 1) per = 100000;
+                fclose(g);
+            }
+            if (quota > 0 && per > 0 && (quota + per / 2) / per < n) n = (int)std::max<long long>(1, (quota + per / 2) / per);
+        }
+        return n < 1 ? 1 : n;
+    }();
+    return cap > 0 && granted > cap ? cap : granted;
+}
 
 extern "C" int bm25x_device_count(void) {
     int n = 0;
@@ -291,7 +320,7 @@ static int index_begin(const BuildMeta &m, int device, bm25x_index **ixp) {
     std::vector<uint8_t> h_fn(N);
     uint64_t sum_len = 0;
     if (m.doc_len) {
-#pragma omp parallel for reduction(+ : sum_len)
+#pragma omp parallel for reduction(+ : sum_len) num_threads(bm25x_host_threads(0))
         for (uint32_t d = 0; d < N; d++) {
             sum_len += m.doc_len[d];
             h_fn[d] = bm25x_length_to_fieldnorm(m.doc_len[d]);
@@ -468,7 +497,7 @@ extern "C" int bm25x_index_create(const bm25x_corpus *c, int device, bm25x_index
 
     // ---- host-side validation of the CSR (the reference panics with "data corruption") ----
     int bad = 0;  // 1 = ordering/ranges, 2 = tf too large
-#pragma omp parallel for schedule(dynamic, 256) reduction(| : bad)
+#pragma omp parallel for schedule(dynamic, 256) reduction(| : bad) num_threads(bm25x_host_threads(0))
     for (uint32_t t = 0; t < T; t++) {
         uint64_t p0 = c->post_off[t], p1 = c->post_off[t + 1];
         if (p1 < p0 || p1 > P) {
@@ -533,7 +562,7 @@ extern "C" int bm25x_index_create_from_blocks(const bm25x_blocks *c, int device,
     std::vector<uint32_t> df(T);
     uint64_t P = 0;
     int bad = 0;
-#pragma omp parallel for schedule(dynamic, 256) reduction(| : bad) reduction(+ : P)
+#pragma omp parallel for schedule(dynamic, 256) reduction(| : bad) reduction(+ : P) num_threads(bm25x_host_threads(0))
     for (uint32_t t = 0; t < T; t++) {
         const uint64_t b0 = c->term_blk_off[t], b1 = c->term_blk_off[t + 1];
         if (b1 < b0 || b1 > NB) {

@@ -232,7 +232,8 @@ extern "C" int bm25x_batch_prepare(bm25x_index *ix, uint32_t nq, const uint32_t 
     std::vector<uint32_t> canon(n_raw ? n_raw : 1);
     std::vector<uint32_t> live(nq ? nq : 1);  // live terms of query i
     int bad_query = -1, bad_kind = 0;
-#pragma omp parallel for schedule(static, 1024)
+    const int nthr = nq < 4096 ? 1 : bm25x_host_threads(16);  // small batches: a parallel region costs more than the loop
+#pragma omp parallel for schedule(static, 1024) num_threads(nthr)
     for (uint32_t i = 0; i < nq; ++i) {
         if (q_off[i + 1] < q_off[i]) {
 #pragma omp critical
@@ -334,7 +335,7 @@ extern "C" int bm25x_batch_prepare(bm25x_index *ix, uint32_t nq, const uint32_t 
     }
     uint64_t postings = 0;
     // ---- pass 2 (parallel): scatter into the staging buffer ----
-#pragma omp parallel for schedule(static, 1024) reduction(+ : postings)
+#pragma omp parallel for schedule(static, 1024) reduction(+ : postings) num_threads(nthr)
     for (uint32_t i = 0; i < nq; ++i) {
         const uint32_t m = live[i];
         if (!m) continue;
@@ -557,7 +558,7 @@ extern "C" int bm25x_merge_topk(uint32_t nq, uint32_t k, const uint32_t *doc_a, 
         bm25x_set_error("bm25x_merge_topk: null argument (f64 scores of both lists are required)");
         return BM25X_ERR_INVALID;
     }
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(nq < 4096 ? 1 : bm25x_host_threads(16))
     for (uint32_t q = 0; q < nq; q++) {
         const size_t base = (size_t)q * k;
         const uint32_t na = std::min(n_a[q], k), nb = std::min(n_b[q], k);

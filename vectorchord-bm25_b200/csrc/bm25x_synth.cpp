@@ -20,6 +20,8 @@
 
 #include "../../include/bm25x.h"
 
+int bm25x_host_threads(int cap);  // bm25x_index.cu: affinity mask capped by the cgroup CPU quota
+
 void bm25x_set_error(const char *fmt, ...);
 
 static inline uint64_t sm64(uint64_t x) {
@@ -85,7 +87,7 @@ extern "C" int bm25x_synth_generate(uint64_t seed, uint32_t n_docs, uint32_t voc
         return BM25X_ERR_INVALID;
     }
     memset(out, 0, sizeof(*out));
-    if (nthreads < 1) nthreads = omp_get_max_threads();
+    if (nthreads < 1) nthreads = bm25x_host_threads(0);
     std::vector<uint64_t> thrv;
     const uint64_t *thr = nullptr;
     if (zipf_s > 0.0) {
