@@ -54,6 +54,9 @@ namespace {
 #ifndef BM25X_RING_DENSE_T
 #define BM25X_RING_DENSE_T 48
 #endif
+#ifndef BM25X_RING_SB
+#define BM25X_RING_SB 0  // 1: single-buffered rings (refill after the chunk, next round prefetched into L2)
+#endif
 #ifndef BM25X_PRUNE_ALPHA
 #define BM25X_PRUNE_ALPHA 0.5  // terms leave the streamed set while the sum of their score bounds stays <= ALPHA · k-th score
 #endif
@@ -77,6 +80,10 @@ struct RCfg {
     static constexpr int TMAX = 32 / (2 * U) < 4 ? 32 / (2 * U) : 4;  // trips between two compactions of the detected postings
     static constexpr int LCAP = TMAX * TRIP + 64;   // candidate list entries, 16 bits each (verified when > 64 are listed)
     static constexpr int INIT = BM25X_RING_INIT;    // postings per run in the very first load (a threshold exists early)
+    // Single-buffered: the whole ring is one window; it is refilled AFTER the chunk (the load is exposed, but it comes
+    // from L2: the bytes were prefetched while the chunk was processed) — half the ring memory per posting in flight,
+    // i.e. more resident warps.  Double-buffered (default): half a ring in flight while the other half is processed.
+    static constexpr bool SB = BM25X_RING_SB != 0;
     static constexpr size_t off_ring = 0;
     static constexpr size_t off_map = off_ring + (size_t)M_ * R * sizeof(Posting);
     static constexpr size_t off_pool_s = off_map + ((size_t)1 << LOG_S);
@@ -378,7 +385,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                 }
             }
             // ---- refill: append what earlier chunks consumed (at most half a ring per round) ----
-            {
+            if (!C::SB) {
                 uint32_t n = 0;
                 if (act && wr < dfpad) {
                     const uint32_t fr = (uint32_t)C::R - (wr - rd);
@@ -671,6 +678,18 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
             rd = e;
             lo = hi;
             if (last) break;
+            if (C::SB) {  // single-buffered: refill everything this chunk freed; the bytes should already sit in L2
+                uint32_t n = 0;
+                if (act && wr < dfpad) {
+                    n = min(((uint32_t)C::R - (wr - rd)) & ~1u, dfpad - wr);
+                    if (n < (uint32_t)C::R / 4 && wr - rd >= (uint32_t)C::R / 4) n = 0;  // no small top-ups
+                }
+                inflight = issue_round(n);
+                if (n > 0 && wr < dfpad) {  // the round after this one: into L2 while this chunk's successor is processed
+                    const uint32_t pf = min((uint32_t)C::R, dfpad - wr) * (uint32_t)sizeof(Posting);
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.post + pbase + wr), "r"(pf) : "memory");
+                }
+            }
         }
         // ---- Results::into_sorted_vec (search.rs:281) ----
         if (pn > 0) pool_cut();
