@@ -231,6 +231,7 @@ extern "C" int bm25x_batch_prepare(bm25x_index *ix, uint32_t nq, const uint32_t 
     const size_t n_raw = nq ? q_off[nq] : 0;
     std::vector<uint32_t> canon(n_raw ? n_raw : 1);
     std::vector<uint32_t> live(nq ? nq : 1);  // live terms of query i
+    std::vector<uint64_t> cost(nq ? nq : 1);  // Σ df of query i
     int bad_query = -1, bad_kind = 0;
     const int nthr = nq < 4096 ? 1 : bm25x_host_threads(16);  // small batches: a parallel region costs more than the loop
 #pragma omp parallel for schedule(static, 1024) num_threads(nthr)
@@ -250,6 +251,9 @@ extern "C" int bm25x_batch_prepare(bm25x_index *ix, uint32_t nq, const uint32_t 
         }
         std::sort(dst, dst + m);
         m = (uint32_t)(std::unique(dst, dst + m) - dst);
+        uint64_t cst = 0;
+        for (uint32_t j = 0; j < m; ++j) cst += h_df[dst[j]];
+        cost[i] = cst;
         if (m > BM25X_MAX_QUERY_TERMS) {
 #pragma omp critical
             { bad_query = (int)i; bad_kind = 2; }
@@ -269,24 +273,56 @@ extern "C" int bm25x_batch_prepare(bm25x_index *ix, uint32_t nq, const uint32_t 
     b->ix = ix;
     b->nq = nq;
     b->k = k;
-    // ---- slots: query i is the slot[i]-th query of its class, its terms start at tpos[i] inside the class ----
+    uint64_t b_qterms = 0;
+    uint32_t b_live = 0;
+    // ---- slots: inside a class the queries are ordered HEAVIEST FIRST (Σ df in power-of-two buckets): the persistent
+    // kernels hand queries out in slot order, so the long head-term queries start first and the tail of the launch is made
+    // of short ones (longest-processing-time scheduling; matters for skewed term frequencies, BASELINE configs[3]).
+    // query i is the slot[i]-th query of its class, its terms start at tpos[i] inside the class ----
     uint8_t cls_of[BM25X_MAX_QUERY_TERMS + 1];
     for (int m = 0, c = 0; m <= BM25X_MAX_QUERY_TERMS; ++m) {
         while (kClasses[c] < m) ++c;
         cls_of[m] = (uint8_t)c;
     }
+    constexpr int NB = 48;  // cost buckets per class
     std::vector<uint32_t> slot(nq ? nq : 1), tpos(nq ? nq : 1);
-    uint32_t cnt_q[kNumClasses] = {0}, cnt_t[kNumClasses] = {0};
+    std::vector<uint8_t> bucket(nq ? nq : 1);
+    static_assert(kNumClasses * NB <= 512, "bucket table");
+    uint32_t bq[kNumClasses * NB] = {0}, bt[kNumClasses * NB] = {0};
     for (uint32_t i = 0; i < nq; ++i) {
         const uint32_t m = live[i];
         if (!m) continue;
         const int c = cls_of[m];
-        slot[i] = cnt_q[c]++;
-        tpos[i] = cnt_t[c];
-        cnt_t[c] += m;
-        b->qterms += m;
-        b->live++;
+        const int b = NB - 1 - std::min<int>(NB - 1, 63 - __builtin_clzll(cost[i] | 1ull));  // 0 = heaviest
+        bucket[i] = (uint8_t)b;
+        bq[c * NB + b]++;
+        bt[c * NB + b] += m;
+        b_qterms += m;
+        b_live++;
     }
+    uint32_t cnt_q[kNumClasses] = {0}, cnt_t[kNumClasses] = {0};
+    for (int c = 0; c < kNumClasses; ++c) {
+        uint32_t q0 = 0, t0 = 0;
+        for (int b = 0; b < NB; ++b) {  // exclusive prefix inside the class
+            const uint32_t nqb = bq[c * NB + b], ntb = bt[c * NB + b];
+            bq[c * NB + b] = q0;
+            bt[c * NB + b] = t0;
+            q0 += nqb;
+            t0 += ntb;
+        }
+        cnt_q[c] = q0;
+        cnt_t[c] = t0;
+    }
+    for (uint32_t i = 0; i < nq; ++i) {
+        const uint32_t m = live[i];
+        if (!m) continue;
+        const int key = cls_of[m] * NB + bucket[i];
+        slot[i] = bq[key]++;
+        tpos[i] = bt[key];
+        bt[key] += m;
+    }
+    b->qterms = b_qterms;
+    b->live = b_live;
     // one staging / device buffer: per class [ids | off | terms | work counter]
     size_t base_ids[kNumClasses], base_off[kNumClasses], base_terms[kNumClasses], base_cnt[kNumClasses], words = 0;
     for (int c = 0; c < kNumClasses; ++c) {

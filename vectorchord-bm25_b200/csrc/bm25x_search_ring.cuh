@@ -3,7 +3,8 @@
 // Replaces the per-query cursor walk of bm25::search (crates/bm25/src/search.rs:137-282) for a whole batch: every
 // warp of the persistent grid is a complete query engine (lane j owns term j of its query).
 //
-//   rings     each term ("run") owns a ring of R postings in shared memory, filled by TMA bulk copies
+//   rings     each term ("run") owns a ring of postings in shared memory (the warp's ring budget is split per query in
+//             proportion to the terms' df), filled by TMA bulk copies
 //             (cp.async.bulk + mbarrier).  A refill appends exactly as many postings as earlier chunks consumed, so
 //             every posting crosses L2 → shared memory once (the v5 kernel re-fetched the unconsumed tail of every
 //             chunk: 1.66 postings loaded per posting consumed).  One refill round is in flight while the previous
@@ -55,7 +56,7 @@ namespace {
 #define BM25X_RING_DENSE_T 48
 #endif
 #ifndef BM25X_RING_SB
-#define BM25X_RING_SB 0  // 1: single-buffered rings (refill after the chunk, next round prefetched into L2)
+#define BM25X_RING_SB 1  // 1: single-buffered rings (refill after the chunk, next round prefetched into L2); 0: double-buffered
 #endif
 #ifndef BM25X_PRUNE_ALPHA
 #define BM25X_PRUNE_ALPHA 0.5  // terms leave the streamed set while the sum of their score bounds stays <= ALPHA · k-th score
@@ -70,9 +71,14 @@ struct RCfg {
     static constexpr bool POOL_GLOBAL = KP_ > 2048;
     static constexpr size_t POOL_SMEM = POOL_GLOBAL ? 0 : (size_t)KP_;
     // ring postings per run: half a ring is in flight while the other half is processed
-    static constexpr int LOG_R = BM25X_RING_LOG_R > 0 ? BM25X_RING_LOG_R : (M_ <= 4 ? 9 : (M_ <= 8 ? 8 : 7));
-    static constexpr int R = 1 << LOG_R;
-    static constexpr uint32_t RM = R - 1;
+    static constexpr int LOG_R = BM25X_RING_LOG_R > 0 ? BM25X_RING_LOG_R : (M_ <= 8 ? 8 : 7);
+    static constexpr int R = 1 << LOG_R;   // ring postings per run when the M runs share the budget evenly
+    // The warp's ring budget (M·R postings) is split per QUERY in proportion to the terms' df (power-of-two rings of
+    // 2^LOG_RMIN .. 2^LOG_RMAX postings): head terms next to rare ones get wide windows instead of M equal rings of
+    // which the rare terms' stay empty; queries with fewer than M terms use the whole budget.
+    static constexpr int BUDGET = M_ * R;
+    static constexpr int LOG_RMIN = 6;
+    static constexpr int LOG_RMAX = (LOG_R + 2 > 10 ? 10 : LOG_R + 2) > LOG_R ? (LOG_R + 2 > 10 ? 10 : LOG_R + 2) : LOG_R;
     static constexpr int LOG_S = M_ == 1 ? 8 : BM25X_RING_LOG_S;  // presence map bytes = dense accumulator bytes (unused for one term)
     static constexpr uint32_t ACC_DOCS = (1u << LOG_S) / 4u;
     static constexpr int U = BM25X_RING_U;          // 16-byte shared loads (2 postings) per lane and trip
@@ -95,11 +101,12 @@ struct RCfg {
     static constexpr size_t off_s1f = 0;  // CTA-shared: 1 KiB table first, then the warps
     static constexpr size_t shared_bytes = 1024;
     static constexpr int WARPS_FIT = (int)((227 * 1024 - shared_bytes) / warp_bytes);
-    static constexpr int WARPS = WARPS_FIT > BM25X_RING_MAXWARPS ? BM25X_RING_MAXWARPS : WARPS_FIT;
+    static constexpr int MAXW = M_ == 1 ? (BM25X_RING_MAXWARPS > 20 ? BM25X_RING_MAXWARPS : 20) : BM25X_RING_MAXWARPS;
+    static constexpr int WARPS = WARPS_FIT > MAXW ? MAXW : WARPS_FIT;
     static constexpr size_t total = shared_bytes + warp_bytes * WARPS;
     static constexpr int THREADS = WARPS * 32;
     static_assert(WARPS >= 1, "one warp must fit");
-    static_assert(R <= 1024 && M_ <= 32 && ((1u << LOG_S) / 4u) <= 32768u,
+    static_assert(LOG_RMAX <= 10 && LOG_R >= LOG_RMIN && M_ <= 32 && ((1u << LOG_S) / 4u) <= 32768u,
                   "entry format: bit 15 = dense flavour (15-bit doc offset), else 5-bit run | 10-bit ring position");
     static_assert(ACC_DOCS >= 64, "accumulator too small");
 };
@@ -110,21 +117,22 @@ __device__ __forceinline__ uint32_t ring_slot(uint32_t doc, int log_s) { return 
 // Fixed LOG_R + 1 power-of-two steps, no data-dependent branch: every lane of a verification pass searches the same run,
 // and independent searches interleave (the while-loop form cost 135 warp instructions per search, profiles/r2b).
 template <class C>
-__device__ __forceinline__ uint32_t ring_lower_bound(const Posting *rg, uint32_t a, uint32_t e, uint32_t doc) {
+__device__ __forceinline__ uint32_t ring_lower_bound(const Posting *rg, uint32_t mask, uint32_t a, uint32_t e,
+                                                     uint32_t doc) {
     uint32_t pos = a;  // every posting before pos is < doc
 #pragma unroll
-    for (int s = C::LOG_R; s >= 0; --s) {
+    for (int s = C::LOG_RMAX; s >= 0; --s) {
         const uint32_t probe = pos + (1u << s);
-        if (probe <= e && rg[(probe - 1u) & C::RM].doc < doc) pos = probe;
+        if (probe <= e && rg[(probe - 1u) & mask].doc < doc) pos = probe;
     }
     return pos;
 }
 // posting word of `doc` in [a, e), 0 when absent
 template <class C>
-__device__ __forceinline__ uint32_t ring_find(const Posting *rg, uint32_t a, uint32_t e, uint32_t doc) {
-    const uint32_t l = ring_lower_bound<C>(rg, a, e, doc);
+__device__ __forceinline__ uint32_t ring_find(const Posting *rg, uint32_t mask, uint32_t a, uint32_t e, uint32_t doc) {
+    const uint32_t l = ring_lower_bound<C>(rg, mask, a, e, doc);
     if (l < e) {
-        const Posting v = rg[l & C::RM];
+        const Posting v = rg[l & mask];
         if (v.doc == doc) return v.w;
     }
     return 0u;
@@ -199,7 +207,6 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
     const float s1min = p.s1f_min;
     uint32_t parity = 0;  // mbarrier phase parity
     uint32_t gen = 0;     // generation tag of the chunk (1..255), never reset: stale tags cost false alarms only
-    Posting *const myring = rings + (size_t)(lane < C::M ? lane : 0) * C::R;
 
     for (;;) {
         int qi = 0;
@@ -225,6 +232,53 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
             s0d = p.s0d[term];
             ubd = p.ubd[term];
         }
+        // ---- ring sizes of this query: ∝ df, powers of two, Σ <= BUDGET (lane j: 2^rlog postings at rings + rbase) ----
+        uint32_t rlog = 0, rbase = 0;
+        {
+            unsigned long long sumdf = dfj;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sumdf += __shfl_xor_sync(FULL, sumdf, o);
+            uint32_t size = 0;
+            if (lane < (int)m) {
+                const uint32_t share = (uint32_t)(((unsigned long long)C::BUDGET * dfj) / sumdf);
+                rlog = share > 1u ? 31u - (uint32_t)__clz(share) : 0u;
+                rlog = min(max(rlog, (uint32_t)C::LOG_RMIN), (uint32_t)C::LOG_RMAX);
+                while (rlog > (uint32_t)C::LOG_RMIN && (1u << (rlog - 1u)) >= dfpad) rlog--;  // no larger than the list
+                size = 1u << rlog;
+            }
+            uint32_t used = __reduce_add_sync(FULL, size);
+            while (used > (uint32_t)C::BUDGET) {  // the minimum sizes of many rare terms can overshoot: halve the largest ring
+                const uint32_t big = __reduce_max_sync(FULL, size);
+                const uint32_t who = __ballot_sync(FULL, size == big);
+                if (lane == __ffs(who) - 1) {
+                    rlog--;
+                    size >>= 1;
+                }
+                used -= big >> 1;
+            }
+            // hand the rest of the budget to the runs with the most postings per ring slot (one doubling per round)
+            for (;;) {
+                const bool can = lane < (int)m && rlog < (uint32_t)C::LOG_RMAX && size < dfpad && used + size <= (uint32_t)C::BUDGET;
+                const uint32_t key = can ? (dfj >> rlog) + 1u : 0u;
+                const uint32_t best = __reduce_max_sync(FULL, key);
+                if (best == 0u) break;
+                const uint32_t who = __ballot_sync(FULL, key == best);
+                if (lane == __ffs(who) - 1) {
+                    rlog++;
+                    size <<= 1;
+                }
+                used += __shfl_sync(FULL, size, __ffs(who) - 1) >> 1;
+            }
+            uint32_t incl = size;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += v;
+            }
+            rbase = incl - size;
+        }
+        const uint32_t rsize = lane < (int)m ? 1u << rlog : 2u, rmask = rsize - 1u;
+        Posting *const myring = rings + rbase;
         uint32_t rd = 0, wr = 0;  // my run: postings [0, rd) consumed, [rd, wr) in the ring (wr: landed at the next wait)
         uint32_t lo = 0;          // every posting with doc < lo has been consumed
         // MaxScore pruning (warp-uniform): terms in ne_mask are no longer streamed; ub_ne = Σ of their score bounds
@@ -299,8 +353,8 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
             if (lane == 0) mbar_arrive_expect_tx(bar, total * (uint32_t)sizeof(Posting));
             __syncwarp();
             if (n > 0) {
-                const uint32_t off = wr & C::RM;
-                const uint32_t n1 = min(n, (uint32_t)C::R - off);
+                const uint32_t off = wr & rmask;
+                const uint32_t n1 = min(n, rsize - off);
                 const Posting *src = p.post + pbase + wr;
                 tma_load_1d(myring + off, src, n1 * (uint32_t)sizeof(Posting), bar);
                 if (n > n1) tma_load_1d(myring, src + n1, (n - n1) * (uint32_t)sizeof(Posting), bar);
@@ -361,11 +415,43 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
             const bool act = lane < (int)m && !((ne_mask >> lane) & 1u);
             const uint32_t avail_e = min(wr, dfj);
             uint32_t limit = INF;  // runs with postings left in HBM bound the window by their last landed document
-            if (act && wr < dfj) limit = myring[(wr - 1u) & C::RM].doc;
+            if (act && wr < dfj) limit = myring[(wr - 1u) & rmask].doc;
             uint32_t hi = __reduce_min_sync(FULL, limit);
             bool last = hi == INF;
             uint32_t e = rd;
-            if (act) e = last ? avail_e : ring_lower_bound<C>(myring, rd, avail_e, hi);
+            if constexpr (C::M <= 4) {
+                // few runs: the whole warp finds each run's window end in two 32-way rounds (ballots) instead of one lane
+                // walking LOG_RMAX + 1 dependent probes — the same instruction count, a fifth of the latency
+#pragma unroll
+                for (int j = 0; j < C::M; ++j) {
+                    if (j < (int)m) {
+                        const uint32_t a = __shfl_sync(FULL, rd, j), b = __shfl_sync(FULL, avail_e, j);
+                        const uint32_t jb = __shfl_sync(FULL, rbase, j), jm = __shfl_sync(FULL, rmask, j);
+                        uint32_t res = b;
+                        if (!((ne_mask >> j) & 1u) && !last && b > a) {  // warp-uniform
+                            const Posting *rgj = rings + jb;
+                            const uint32_t n = b - a;
+                            uint32_t t0 = a, t1 = b;
+                            bool whole = false;
+                            if (n > 32u) {  // round 1: lane l looks at the last posting of the l-th of 32 slices
+                                const uint32_t s1 = a + ((n * (uint32_t)(lane + 1)) >> 5);
+                                const uint32_t c = __popc(__ballot_sync(FULL, rgj[(s1 - 1u) & jm].doc < hi));
+                                whole = c == 32u;
+                                t0 = a + ((n * c) >> 5);
+                                t1 = a + ((n * (c + 1u)) >> 5);
+                            }
+                            if (!whole) {   // round 2: the (at most 32) postings of the slice that holds the end
+                                const uint32_t i = t0 + (uint32_t)lane;
+                                res = t0 + __popc(__ballot_sync(FULL, i < t1 && rgj[i & jm].doc < hi));
+                            }
+                        }
+                        if (lane == j) e = res;
+                    }
+                }
+                if (!act) e = rd;
+            } else if (act) {
+                e = last ? avail_e : ring_lower_bound<C>(myring, rmask, rd, avail_e, hi);
+            }
             // ---- dense or sparse?  (expected number of documents held by two runs in this window) ----
             bool dense = false;
             uint32_t span = 0;
@@ -374,24 +460,24 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                 const uint32_t S = __reduce_add_sync(FULL, n);
                 const uint32_t S2 = __reduce_add_sync(FULL, n * n);
                 uint32_t hi_eff = hi;
-                if (last) hi_eff = __reduce_max_sync(FULL, n ? myring[(e - 1u) & C::RM].doc + 1u : 0u);
+                if (last) hi_eff = __reduce_max_sync(FULL, n ? myring[(e - 1u) & rmask].doc + 1u : 0u);
                 span = hi_eff > lo ? hi_eff - lo : 0u;
                 dense = (unsigned long long)S * S - S2 > 2ull * BM25X_RING_DENSE_T * (unsigned long long)span;
                 if (dense && span > C::ACC_DOCS) {  // clamp the window to the accumulator: consume the rings partially
                     hi = lo < INF - 1u - C::ACC_DOCS ? lo + C::ACC_DOCS : INF - 1u;
                     last = false;
                     span = C::ACC_DOCS;
-                    if (act) e = ring_lower_bound<C>(myring, rd, e, hi);
+                    if (act) e = ring_lower_bound<C>(myring, rmask, rd, e, hi);
                 }
             }
             // ---- refill: append what earlier chunks consumed (at most half a ring per round) ----
             if (!C::SB) {
                 uint32_t n = 0;
                 if (act && wr < dfpad) {
-                    const uint32_t fr = (uint32_t)C::R - (wr - rd);
-                    n = min(min(fr, (uint32_t)C::R / 2) & ~1u, dfpad - wr);
+                    const uint32_t fr = rsize - (wr - rd);
+                    n = min(min(fr, rsize / 2) & ~1u, dfpad - wr);
                     // no small top-ups while the run still holds a quarter ring beyond this chunk
-                    if (n < (uint32_t)C::R / 8 && wr - e >= (uint32_t)C::R / 4) n = 0;
+                    if (n < rsize / 8 && wr - e >= rsize / 4) n = 0;
                 }
                 inflight = issue_round(n);
             }
@@ -407,7 +493,8 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                     Posting own;
                     own.doc = 0;
                     own.w = 0;
-                    if (has && !by_doc) own = rings[(size_t)j * C::R + (ent & 0x3FFu)];
+                    const uint32_t jbase = __shfl_sync(FULL, rbase, j & 31u);
+                    if (has && !by_doc) own = rings[jbase + (ent & 0x3FFu)];
                     const uint32_t doc = by_doc ? lo + (ent & 0x7FFFu) : own.doc;
                     float F = 0.f;
                     uint32_t cnt = 0, sig = SIG_NONE;
@@ -416,15 +503,16 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                     uint32_t wv[KEEPW ? C::M : 1];
 #pragma unroll
                     for (int i = 0; i < (KEEPW ? C::M : 1); ++i) wv[i] = 0u;
-                    auto holder = [&](int i, uint32_t ai, uint32_t ei) -> uint32_t {
-                        return (uint32_t)i == j ? own.w : ring_find<C>(rings + (size_t)i * C::R, ai, ei, doc);
+                    auto holder = [&](int i, uint32_t ib, uint32_t im, uint32_t ai, uint32_t ei) -> uint32_t {
+                        return (uint32_t)i == j ? own.w : ring_find<C>(rings + ib, im, ai, ei, doc);
                     };
                     auto filter_term = [&](int i) {
                         const uint32_t ai = __shfl_sync(FULL, rd, i), ei = __shfl_sync(FULL, e, i);
+                        const uint32_t ib = __shfl_sync(FULL, rbase, i), im = __shfl_sync(FULL, rmask, i);
                         const float s0 = __shfl_sync(FULL, s0f, i);
                         uint32_t wi = 0u;
                         if (has && !((ne_mask >> i) & 1u)) {
-                            wi = holder(i, ai, ei);
+                            wi = holder(i, ib, im, ai, ei);
                             if (wi) {
                                 F += score_f32(wi, s0, s1f);
                                 cnt++;
@@ -513,8 +601,9 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
 #pragma unroll 1
                             for (int i = 0; i < (int)m; ++i) {
                                 const uint32_t ai = __shfl_sync(FULL, rd, i), ei = __shfl_sync(FULL, e, i);
+                                const uint32_t ib = __shfl_sync(FULL, rbase, i), im = __shfl_sync(FULL, rmask, i);
                                 uint32_t wi = 0u;
-                                if (keep && !((ne_mask >> i) & 1u)) wi = holder(i, ai, ei);
+                                if (keep && !((ne_mask >> i) & 1u)) wi = holder(i, ib, im, ai, ei);
                                 exact_term(i, wi);
                             }
                         }
@@ -541,7 +630,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
             // sparse window: runs in ascending order; each run tests its documents against the marks of the earlier runs,
             // then marks them.  dense window: scores summed in an f32 accumulator indexed by doc - lo (in the map's
             // memory; docs are distinct inside a run: plain read-modify-write, __syncwarp between runs), then scanned.
-            uint32_t todo = 0u, ra = 0u, ree = 0u, rnj = 0u, wl = 0u, tw = 0u, tdk = 0u, pb = 0u, genv = 0u, dbase = 0u;
+            uint32_t todo = 0u, ra = 0u, ree = 0u, rnj = 0u, wl = 0u, tw = 0u, tdk = 0u, pb = 0u, genv = 0u, dbase = 0u, rm = 1u;
             int rj = -1, variant = 0;
             bool first = true, multi = false;
             const uint4 *rg = nullptr;
@@ -560,9 +649,10 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                     td &= td - 1u;
                     const uint32_t a = __shfl_sync(FULL, rd, j), ee = __shfl_sync(FULL, e, j);
                     const float s0 = __shfl_sync(FULL, s0f, j);
-                    const Posting *rgp = rings + (size_t)j * C::R;
+                    const Posting *rgp = rings + __shfl_sync(FULL, rbase, j);
+                    const uint32_t jm = __shfl_sync(FULL, rmask, j);
                     for (uint32_t i = a + lane; i < ee; i += 32) {
-                        const Posting v = rgp[i & C::RM];
+                        const Posting v = rgp[i & jm];
                         acc[v.doc - lo] += score_f32(v.w, s0, s1f);
                     }
                     __syncwarp();
@@ -582,7 +672,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
 #pragma unroll
                     for (int u = 0; u < C::U; ++u) {
                         ix[u] = pb + 2u * (uint32_t)(lane + 32 * u);
-                        q[u] = rg[(ix[u] >> 1) & (C::RM >> 1)];
+                        q[u] = rg[(ix[u] >> 1) & (rm >> 1)];
                     }
                     uint32_t bits = 0u;
                     auto body = [&](auto check_c) {
@@ -616,7 +706,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                         hm &= hm - 1u;
                         const uint32_t t = bpos / (2 * C::U), sl = bpos % (2 * C::U);
                         const uint32_t idx = pb0 + t * C::TRIP + 2u * (uint32_t)(lane + 32 * (sl >> 1)) + (sl & 1u);
-                        cand[nc + __popc(bal & lt_mask)] = (uint16_t)(((uint32_t)rj << 10) | (idx & C::RM));
+                        cand[nc + __popc(bal & lt_mask)] = (uint16_t)(((uint32_t)rj << 10) | (idx & rm));
                     }
                     nc += __popc(bal);
                 }
@@ -639,7 +729,8 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                             wl = __shfl_sync(FULL, wlim, rj);
                             tw = __shfl_sync(FULL, tiew, rj);
                             rnj = ree - ra;
-                            rg = (const uint4 *)(rings + (size_t)rj * C::R);
+                            rg = (const uint4 *)(rings + __shfl_sync(FULL, rbase, rj));
+                            rm = __shfl_sync(FULL, rmask, rj);
                             tdk = f.tie_dk;  // snapshot with tw: a stale (looser) pair stays valid, thresholds only tighten
                             pb = ra & ~1u;
                             // wl == ~0: no single-term posting of this run can pass → the loop variant without the test
@@ -681,12 +772,12 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
             if (C::SB) {  // single-buffered: refill everything this chunk freed; the bytes should already sit in L2
                 uint32_t n = 0;
                 if (act && wr < dfpad) {
-                    n = min(((uint32_t)C::R - (wr - rd)) & ~1u, dfpad - wr);
-                    if (n < (uint32_t)C::R / 4 && wr - rd >= (uint32_t)C::R / 4) n = 0;  // no small top-ups
+                    n = min((rsize - (wr - rd)) & ~1u, dfpad - wr);
+                    if (n < rsize / 4 && wr - rd >= rsize / 4) n = 0;  // no small top-ups
                 }
                 inflight = issue_round(n);
                 if (n > 0 && wr < dfpad) {  // the round after this one: into L2 while this chunk's successor is processed
-                    const uint32_t pf = min((uint32_t)C::R, dfpad - wr) * (uint32_t)sizeof(Posting);
+                    const uint32_t pf = min(rsize, dfpad - wr) * (uint32_t)sizeof(Posting);
                     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.post + pbase + wr), "r"(pf) : "memory");
                 }
             }
