@@ -58,6 +58,9 @@ namespace {
 #ifndef BM25X_RING_SB
 #define BM25X_RING_SB 1  // 1: single-buffered rings (refill after the chunk, next round prefetched into L2); 0: double-buffered
 #endif
+#ifndef BM25X_RING_ADAPT
+#define BM25X_RING_ADAPT 1  // 1: ring sizes per query ∝ df; 0: M equal rings
+#endif
 #ifndef BM25X_PRUNE_ALPHA
 #define BM25X_PRUNE_ALPHA 0.5  // terms leave the streamed set while the sum of their score bounds stays <= ALPHA · k-th score
 #endif
@@ -116,21 +119,21 @@ __device__ __forceinline__ uint32_t ring_slot(uint32_t doc, int log_s) { return 
 // lower_bound of `doc` in ring positions [a, e) (posting indices of the term; the ring holds index i at i & RM).
 // Fixed LOG_R + 1 power-of-two steps, no data-dependent branch: every lane of a verification pass searches the same run,
 // and independent searches interleave (the while-loop form cost 135 warp instructions per search, profiles/r2b).
-template <class C>
+template <class C, int TOP = C::LOG_RMAX>
 __device__ __forceinline__ uint32_t ring_lower_bound(const Posting *rg, uint32_t mask, uint32_t a, uint32_t e,
                                                      uint32_t doc) {
     uint32_t pos = a;  // every posting before pos is < doc
 #pragma unroll
-    for (int s = C::LOG_RMAX; s >= 0; --s) {
+    for (int s = TOP; s >= 0; --s) {
         const uint32_t probe = pos + (1u << s);
         if (probe <= e && rg[(probe - 1u) & mask].doc < doc) pos = probe;
     }
     return pos;
 }
 // posting word of `doc` in [a, e), 0 when absent
-template <class C>
+template <class C, int TOP = C::LOG_RMAX>
 __device__ __forceinline__ uint32_t ring_find(const Posting *rg, uint32_t mask, uint32_t a, uint32_t e, uint32_t doc) {
-    const uint32_t l = ring_lower_bound<C>(rg, mask, a, e, doc);
+    const uint32_t l = ring_lower_bound<C, TOP>(rg, mask, a, e, doc);
     if (l < e) {
         const Posting v = rg[l & mask];
         if (v.doc == doc) return v.w;
@@ -239,6 +242,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) sumdf += __shfl_xor_sync(FULL, sumdf, o);
             uint32_t size = 0;
+            if (!BM25X_RING_ADAPT) sumdf = (unsigned long long)dfj * C::M;  // equal shares
             if (lane < (int)m) {
                 const uint32_t share = (uint32_t)(((unsigned long long)C::BUDGET * dfj) / sumdf);
                 rlog = share > 1u ? 31u - (uint32_t)__clz(share) : 0u;
@@ -258,7 +262,8 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
             }
             // hand the rest of the budget to the runs with the most postings per ring slot (one doubling per round)
             for (;;) {
-                const bool can = lane < (int)m && rlog < (uint32_t)C::LOG_RMAX && size < dfpad && used + size <= (uint32_t)C::BUDGET;
+                const bool can = BM25X_RING_ADAPT && lane < (int)m && rlog < (uint32_t)C::LOG_RMAX && size < dfpad &&
+                                 used + size <= (uint32_t)C::BUDGET;
                 const uint32_t key = can ? (dfj >> rlog) + 1u : 0u;
                 const uint32_t best = __reduce_max_sync(FULL, key);
                 if (best == 0u) break;
@@ -278,6 +283,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
             rbase = incl - size;
         }
         const uint32_t rsize = lane < (int)m ? 1u << rlog : 2u, rmask = rsize - 1u;
+        const bool small_rings = __reduce_max_sync(FULL, rlog) <= (uint32_t)C::LOG_R;  // searches need LOG_R + 1 steps only
         Posting *const myring = rings + rbase;
         uint32_t rd = 0, wr = 0;  // my run: postings [0, rd) consumed, [rd, wr) in the ring (wr: landed at the next wait)
         uint32_t lo = 0;          // every posting with doc < lo has been consumed
@@ -419,38 +425,10 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
             uint32_t hi = __reduce_min_sync(FULL, limit);
             bool last = hi == INF;
             uint32_t e = rd;
-            if constexpr (C::M <= 4) {
-                // few runs: the whole warp finds each run's window end in two 32-way rounds (ballots) instead of one lane
-                // walking LOG_RMAX + 1 dependent probes — the same instruction count, a fifth of the latency
-#pragma unroll
-                for (int j = 0; j < C::M; ++j) {
-                    if (j < (int)m) {
-                        const uint32_t a = __shfl_sync(FULL, rd, j), b = __shfl_sync(FULL, avail_e, j);
-                        const uint32_t jb = __shfl_sync(FULL, rbase, j), jm = __shfl_sync(FULL, rmask, j);
-                        uint32_t res = b;
-                        if (!((ne_mask >> j) & 1u) && !last && b > a) {  // warp-uniform
-                            const Posting *rgj = rings + jb;
-                            const uint32_t n = b - a;
-                            uint32_t t0 = a, t1 = b;
-                            bool whole = false;
-                            if (n > 32u) {  // round 1: lane l looks at the last posting of the l-th of 32 slices
-                                const uint32_t s1 = a + ((n * (uint32_t)(lane + 1)) >> 5);
-                                const uint32_t c = __popc(__ballot_sync(FULL, rgj[(s1 - 1u) & jm].doc < hi));
-                                whole = c == 32u;
-                                t0 = a + ((n * c) >> 5);
-                                t1 = a + ((n * (c + 1u)) >> 5);
-                            }
-                            if (!whole) {   // round 2: the (at most 32) postings of the slice that holds the end
-                                const uint32_t i = t0 + (uint32_t)lane;
-                                res = t0 + __popc(__ballot_sync(FULL, i < t1 && rgj[i & jm].doc < hi));
-                            }
-                        }
-                        if (lane == j) e = res;
-                    }
-                }
-                if (!act) e = rd;
-            } else if (act) {
-                e = last ? avail_e : ring_lower_bound<C>(myring, rmask, rd, avail_e, hi);
+            if (act) {
+                if (last) e = avail_e;
+                else if (small_rings) e = ring_lower_bound<C, C::LOG_R>(myring, rmask, rd, avail_e, hi);
+                else e = ring_lower_bound<C>(myring, rmask, rd, avail_e, hi);
             }
             // ---- dense or sparse?  (expected number of documents held by two runs in this window) ----
             bool dense = false;
@@ -504,7 +482,9 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
 #pragma unroll
                     for (int i = 0; i < (KEEPW ? C::M : 1); ++i) wv[i] = 0u;
                     auto holder = [&](int i, uint32_t ib, uint32_t im, uint32_t ai, uint32_t ei) -> uint32_t {
-                        return (uint32_t)i == j ? own.w : ring_find<C>(rings + ib, im, ai, ei, doc);
+                        return (uint32_t)i == j ? own.w
+                                                : (small_rings ? ring_find<C, C::LOG_R>(rings + ib, im, ai, ei, doc)
+                                                               : ring_find<C>(rings + ib, im, ai, ei, doc));
                     };
                     auto filter_term = [&](int i) {
                         const uint32_t ai = __shfl_sync(FULL, rd, i), ei = __shfl_sync(FULL, e, i);
@@ -522,7 +502,52 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                         }
                         return wi;
                     };
-                    if constexpr (KEEPW) {
+                    if constexpr (C::M <= 4) {
+                        // few runs: the binary searches of one candidate in all runs advance TOGETHER, one step of each per
+                        // round — independent dependent-load chains overlap instead of queueing behind each other
+                        uint32_t pa[C::M], pe[C::M], pbs[C::M], pm[C::M];
+#pragma unroll
+                        for (int i = 0; i < C::M; ++i) {
+                            pa[i] = __shfl_sync(FULL, rd, i);
+                            pe[i] = __shfl_sync(FULL, e, i);
+                            pbs[i] = __shfl_sync(FULL, rbase, i);
+                            pm[i] = __shfl_sync(FULL, rmask, i);
+                            // runs that are not searched for this candidate: empty range
+                            if (i >= (int)m || !has || (uint32_t)i == j || ((ne_mask >> i) & 1u)) pe[i] = pa[i];
+                        }
+                        auto steps = [&](auto top_c) {
+#pragma unroll
+                            for (int st = decltype(top_c)::value; st >= 0; --st) {
+#pragma unroll
+                                for (int i = 0; i < C::M; ++i) {
+                                    const uint32_t probe = pa[i] + (1u << st);
+                                    if (probe <= pe[i] && rings[pbs[i] + ((probe - 1u) & pm[i])].doc < doc) pa[i] = probe;
+                                }
+                            }
+                        };
+                        if (small_rings) steps(std::integral_constant<int, C::LOG_R>());
+                        else steps(std::integral_constant<int, C::LOG_RMAX>());
+#pragma unroll
+                        for (int i = 0; i < C::M; ++i) {
+                            if (i < (int)m) {
+                                const float s0 = __shfl_sync(FULL, s0f, i);
+                                uint32_t wi = 0u;
+                                if ((uint32_t)i == j) {
+                                    wi = (has && !((ne_mask >> i) & 1u)) ? own.w : 0u;
+                                } else if (pa[i] < pe[i]) {
+                                    const Posting v = rings[pbs[i] + (pa[i] & pm[i])];
+                                    if (v.doc == doc) wi = v.w;
+                                }
+                                if (wi) {
+                                    F += score_f32(wi, s0, s1f);
+                                    cnt++;
+                                    sig = make_sig(i, wi);
+                                    later |= (uint32_t)i > j;
+                                }
+                                wv[i] = wi;
+                            }
+                        }
+                    } else if constexpr (KEEPW) {
 #pragma unroll
                         for (int i = 0; i < C::M; ++i)
                             if (i < (int)m) wv[i] = filter_term(i);
@@ -634,11 +659,16 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
             int rj = -1, variant = 0;
             bool first = true, multi = false;
             const uint4 *rg = nullptr;
+            int myvariant = 0;  // lane j: loop variant of run j in this window (4: single-term test, 2: test, 1: mark)
             if (!dense) {
                 todo = __ballot_sync(FULL, act && e > rd);
                 multi = C::M > 1 && __popc(todo) > 1;
                 if (multi) gen = gen % 255u + 1u;
                 genv = gen;
+                // wlim == ~0: no single-term posting of the run can pass → the loop variant without that test; the first
+                // non-empty run has nothing to test against, the last one nobody to mark for
+                myvariant = (wlim != 0xFFFFFFFFu ? 4 : 0) | (multi && lane != __ffs(todo) - 1 ? 2 : 0) |
+                            (multi && lane != 31 - __clz(todo) ? 1 : 0);
             } else {
                 float *acc = (float *)map;
                 for (uint32_t i = lane; i < (span + 3u) / 4u; i += 32) ((float4 *)acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -733,8 +763,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                             rm = __shfl_sync(FULL, rmask, rj);
                             tdk = f.tie_dk;  // snapshot with tw: a stale (looser) pair stays valid, thresholds only tighten
                             pb = ra & ~1u;
-                            // wl == ~0: no single-term posting of this run can pass → the loop variant without the test
-                            variant = (wl != 0xFFFFFFFFu ? 4 : 0) | (multi && !first ? 2 : 0) | (multi && todo != 0u ? 1 : 0);
+                            variant = __shfl_sync(FULL, myvariant, rj);
                             if (variant == 0) pb = ree;  // nothing to learn from this run in this window
                         }
                     }
