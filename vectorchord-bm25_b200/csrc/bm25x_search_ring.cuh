@@ -58,6 +58,9 @@ namespace {
 #ifndef BM25X_RING_SB
 #define BM25X_RING_SB 1  // 1: single-buffered rings (refill after the chunk, next round prefetched into L2); 0: double-buffered
 #endif
+#ifndef BM25X_RING_SUBT
+#define BM25X_RING_SUBT 640  // classes of 8+ terms: postings per map generation (sub-window) — bounds the false alarms
+#endif
 #ifndef BM25X_RING_ADAPT
 #define BM25X_RING_ADAPT 1  // 1: ring sizes per query ∝ df; 0: M equal rings
 #endif
@@ -235,15 +238,21 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
             s0d = p.s0d[term];
             ubd = p.ubd[term];
         }
-        // ---- ring sizes of this query: ∝ df, powers of two, Σ <= BUDGET (lane j: 2^rlog postings at rings + rbase) ----
-        uint32_t rlog = 0, rbase = 0;
-        {
-            unsigned long long sumdf = dfj;
+        // ---- ring sizes: ∝ df over the streamed terms, powers of two, Σ <= BUDGET (lane j: 2^rlog postings at
+        // rings + rbase).  Called at query start and again whenever terms leave the streamed set (their rings go back to
+        // the budget).
+        uint32_t rlog = 0, rbase = 0, rsize = 2u, rmask = 1u;
+        bool small_rings = true;  // every ring <= 2^LOG_R postings: searches need LOG_R + 1 steps only
+        Posting *myring = rings;
+        auto alloc_rings = [&](uint32_t streamed) {
+            const bool mine = lane < (int)m && ((streamed >> lane) & 1u);
+            unsigned long long sumdf = mine ? dfj : 0u;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) sumdf += __shfl_xor_sync(FULL, sumdf, o);
-            uint32_t size = 0;
             if (!BM25X_RING_ADAPT) sumdf = (unsigned long long)dfj * C::M;  // equal shares
-            if (lane < (int)m) {
+            uint32_t size = 0;
+            rlog = 0;
+            if (mine) {
                 const uint32_t share = (uint32_t)(((unsigned long long)C::BUDGET * dfj) / sumdf);
                 rlog = share > 1u ? 31u - (uint32_t)__clz(share) : 0u;
                 rlog = min(max(rlog, (uint32_t)C::LOG_RMIN), (uint32_t)C::LOG_RMAX);
@@ -260,19 +269,17 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                 }
                 used -= big >> 1;
             }
-            // hand the rest of the budget to the runs with the most postings per ring slot (one doubling per round)
+            // the rest of the budget: double EVERY ring that can still grow, as long as all of them fit (keeps the
+            // proportions: equal terms keep equal rings)
             for (;;) {
-                const bool can = BM25X_RING_ADAPT && lane < (int)m && rlog < (uint32_t)C::LOG_RMAX && size < dfpad &&
-                                 used + size <= (uint32_t)C::BUDGET;
-                const uint32_t key = can ? (dfj >> rlog) + 1u : 0u;
-                const uint32_t best = __reduce_max_sync(FULL, key);
-                if (best == 0u) break;
-                const uint32_t who = __ballot_sync(FULL, key == best);
-                if (lane == __ffs(who) - 1) {
+                const bool can = BM25X_RING_ADAPT && mine && rlog < (uint32_t)C::LOG_RMAX && size < dfpad;
+                const uint32_t extra = __reduce_add_sync(FULL, can ? size : 0u);
+                if (extra == 0u || used + extra > (uint32_t)C::BUDGET) break;
+                if (can) {
                     rlog++;
                     size <<= 1;
                 }
-                used += __shfl_sync(FULL, size, __ffs(who) - 1) >> 1;
+                used += extra;
             }
             uint32_t incl = size;
 #pragma unroll
@@ -281,10 +288,12 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                 if (lane >= o) incl += v;
             }
             rbase = incl - size;
-        }
-        const uint32_t rsize = lane < (int)m ? 1u << rlog : 2u, rmask = rsize - 1u;
-        const bool small_rings = __reduce_max_sync(FULL, rlog) <= (uint32_t)C::LOG_R;  // searches need LOG_R + 1 steps only
-        Posting *const myring = rings + rbase;
+            rsize = mine ? size : 2u;
+            rmask = rsize - 1u;
+            myring = rings + rbase;
+            small_rings = __reduce_max_sync(FULL, rlog) <= (uint32_t)C::LOG_R;
+        };
+        alloc_rings(FULL);
         uint32_t rd = 0, wr = 0;  // my run: postings [0, rd) consumed, [rd, wr) in the ring (wr: landed at the next wait)
         uint32_t lo = 0;          // every posting with doc < lo has been consumed
         // MaxScore pruning (warp-uniform): terms in ne_mask are no longer streamed; ub_ne = Σ of their score bounds
@@ -416,7 +425,23 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                     ub_ne += ub;
                     changed = true;
                 }
-                if (changed) refresh_filter();
+                if (changed) {
+                    refresh_filter();
+                    if (BM25X_RING_ADAPT && C::SB) {
+                        // the pruned terms' rings go back to the budget: the streamed terms get wider windows.  Their rings
+                        // move, so what they held beyond rd is fetched again (a few hundred postings, a few times per query)
+                        alloc_rings(~ne_mask);
+                        uint32_t n = 0;
+                        if (lane < (int)m && !((ne_mask >> lane) & 1u)) {
+                            wr = rd & ~1u;
+                            n = min(rsize, dfpad - wr);
+                        }
+                        if (issue_round(n)) {
+                            mbar_wait(bar, parity);
+                            parity ^= 1u;
+                        }
+                    }
+                }
             }
             const bool act = lane < (int)m && !((ne_mask >> lane) & 1u);
             const uint32_t avail_e = min(wr, dfj);
@@ -432,10 +457,11 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
             }
             // ---- dense or sparse?  (expected number of documents held by two runs in this window) ----
             bool dense = false;
-            uint32_t span = 0;
+            uint32_t span = 0, chunk_postings = 0;
             if (C::M > 1) {
                 const uint32_t n = e - rd;
                 const uint32_t S = __reduce_add_sync(FULL, n);
+                chunk_postings = S;
                 const uint32_t S2 = __reduce_add_sync(FULL, n * n);
                 uint32_t hi_eff = hi;
                 if (last) hi_eff = __reduce_max_sync(FULL, n ? myring[(e - 1u) & rmask].doc + 1u : 0u);
@@ -502,52 +528,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                         }
                         return wi;
                     };
-                    if constexpr (C::M <= 4) {
-                        // few runs: the binary searches of one candidate in all runs advance TOGETHER, one step of each per
-                        // round — independent dependent-load chains overlap instead of queueing behind each other
-                        uint32_t pa[C::M], pe[C::M], pbs[C::M], pm[C::M];
-#pragma unroll
-                        for (int i = 0; i < C::M; ++i) {
-                            pa[i] = __shfl_sync(FULL, rd, i);
-                            pe[i] = __shfl_sync(FULL, e, i);
-                            pbs[i] = __shfl_sync(FULL, rbase, i);
-                            pm[i] = __shfl_sync(FULL, rmask, i);
-                            // runs that are not searched for this candidate: empty range
-                            if (i >= (int)m || !has || (uint32_t)i == j || ((ne_mask >> i) & 1u)) pe[i] = pa[i];
-                        }
-                        auto steps = [&](auto top_c) {
-#pragma unroll
-                            for (int st = decltype(top_c)::value; st >= 0; --st) {
-#pragma unroll
-                                for (int i = 0; i < C::M; ++i) {
-                                    const uint32_t probe = pa[i] + (1u << st);
-                                    if (probe <= pe[i] && rings[pbs[i] + ((probe - 1u) & pm[i])].doc < doc) pa[i] = probe;
-                                }
-                            }
-                        };
-                        if (small_rings) steps(std::integral_constant<int, C::LOG_R>());
-                        else steps(std::integral_constant<int, C::LOG_RMAX>());
-#pragma unroll
-                        for (int i = 0; i < C::M; ++i) {
-                            if (i < (int)m) {
-                                const float s0 = __shfl_sync(FULL, s0f, i);
-                                uint32_t wi = 0u;
-                                if ((uint32_t)i == j) {
-                                    wi = (has && !((ne_mask >> i) & 1u)) ? own.w : 0u;
-                                } else if (pa[i] < pe[i]) {
-                                    const Posting v = rings[pbs[i] + (pa[i] & pm[i])];
-                                    if (v.doc == doc) wi = v.w;
-                                }
-                                if (wi) {
-                                    F += score_f32(wi, s0, s1f);
-                                    cnt++;
-                                    sig = make_sig(i, wi);
-                                    later |= (uint32_t)i > j;
-                                }
-                                wv[i] = wi;
-                            }
-                        }
-                    } else if constexpr (KEEPW) {
+                    if constexpr (KEEPW) {
 #pragma unroll
                         for (int i = 0; i < C::M; ++i)
                             if (i < (int)m) wv[i] = filter_term(i);
@@ -651,6 +632,21 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                 nc = 0;
             };
 
+            // Classes of 8+ terms unite a few thousand postings per chunk: the presence map would be a quarter full and a
+            // tenth of all postings false alarms.  The chunk is therefore walked in doc SUB-WINDOWS of about SUBT postings,
+            // each with its own map generation (one more boundary search per run and sub-window, lanes in parallel).
+            uint32_t nsub = 1;
+            if (C::M >= 8 && !dense) nsub = min(8u, (chunk_postings + BM25X_RING_SUBT - 1u) / BM25X_RING_SUBT);
+            if (nsub < 1u) nsub = 1u;
+            const uint32_t e_full = e;
+            for (uint32_t sub = 0; sub < nsub; ++sub) {
+            if (nsub > 1u) {
+                e = e_full;
+                if (sub + 1u < nsub) {
+                    const uint32_t hs = lo + (uint32_t)(((unsigned long long)span * (sub + 1u)) / nsub);
+                    e = act ? ring_lower_bound<C>(myring, rmask, rd, e_full, hs) : rd;
+                }
+            }
             // ---- candidate production (resumable) + ONE verification site ----
             // sparse window: runs in ascending order; each run tests its documents against the marks of the earlier runs,
             // then marks them.  dense window: scores summed in an f32 accumulator indexed by doc - lo (in the map's
@@ -796,6 +792,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                 if (nc > 64u || (finished && nc)) verify();
             }
             rd = e;
+            }  // sub-windows
             lo = hi;
             if (last) break;
             if (C::SB) {  // single-buffered: refill everything this chunk freed; the bytes should already sit in L2
