@@ -135,12 +135,7 @@ def measured_traffic(workload, nq, k):
 def kernel_name(tmax, k):
     """The kernel instance the library launches for the widest query class of the workload (bm25x_search.cu)."""
     cls = next(c for c in (1, 2, 3, 4, 8, 16, 32) if c >= tmax)
-    gen = os.environ.get("BM25X_KERNEL", "ring")
-    if gen == "ring":
-        return f"k_search_ring<RCfg<{cls},{64 if k <= 32 else 256 if k <= 224 else 2048}>>"
-    if gen == "wq" and k <= 128 and cls <= 8:
-        return f"k_search_wq<WCfg<{cls},{128 if k <= 32 else 256}>>"
-    return f"k_search<KCfg<{cls}>>"
+    return f"k_search_ring<RCfg<{cls},{64 if k <= 32 else 256 if k <= 224 else 2048 if k <= 1024 else 131072}>>"
 
 
 def hbm_peak():

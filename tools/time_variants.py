@@ -1,8 +1,7 @@
 #!/usr/bin/env python
 """Times library variants / kernel generations side by side on ONE GPU and checks that all return the same bits.
 
-  python tools/time_variants.py NAME[@GEN] ...      NAME = variants/libbm25x_NAME.so ("main" = the in-tree library),
-                                                    GEN  = BM25X_KERNEL value (ring | wq | cta)
+  python tools/time_variants.py NAME ...      NAME = variants/libbm25x_NAME.so ("main" = the in-tree library)
 Env: VAR_DOCS (default 10M), VAR_WORKLOADS (comma list of c3,c3k100,c5mix,c2,c4).  Every variant runs in its own process.
 """
 import hashlib
@@ -64,8 +63,6 @@ def main():
         env = dict(os.environ)
         if name != "main":
             env["BM25X_LIBRARY"] = os.path.join(ROOT, "vectorchord-bm25_b200", "variants", f"libbm25x_{name}.so")
-        if gen:
-            env["BM25X_KERNEL"] = gen
         try:
             p = subprocess.run([sys.executable, __file__, "--one", str(docs)], env=env, capture_output=True, text=True,
                                timeout=int(os.environ.get("VAR_TIMEOUT", 120)))

@@ -4,22 +4,14 @@
 // over 8 KiB pages with Block-max WAND, a persistent grid streams every query's posting lists
 // through shared memory with TMA bulk copies and merges them there.
 //
-//   producer warp  : per query, cuts the doc-id space into chunks whose postings fit one smem stage
-//                    (quota of 128-posting blocks per term ∝ df, boundaries from the per-block
-//                    (first doc, last doc) table = SummaryTuple.{min,max}_document_id), and issues one
-//                    cp.async.bulk per term per chunk, completion on an mbarrier (STAGES-deep ring).
-//   merge threads  : phase 0 buckets the chunk's postings by doc id (T equal-width buckets; one pass,
-//                    no search); phase A: each thread m-way merges its bucket (posting at a time,
-//                    heads in registers), f32 score per doc = Σ s0·tf/(tf+s1[fn]) — the Cache::evaluate
-//                    formula (bm25.rs:355-358) in f32 — and filters against the current k-th score;
-//                    phase B: the few survivors are re-scored in f64 with the reference's exact
-//                    operation order and appended to a pool; the pool is cut back to k by a bitonic
-//                    sort when it fills.  Final order: score desc, doc id asc.
+//   k_search_ring (bm25x_search_ring.cuh): one warp per query, persistent grid.  Every term owns a shared-memory ring
+//   filled by TMA bulk copies; the runs of a doc window are united through a presence map (test against the marks of
+//   the earlier runs, then mark), detected postings are verified by binary search, filtered in f32 and re-scored in
+//   f64 in the reference's operation order; MaxScore pruning with probes of the pruned terms in HBM.
 //
-// Exactness: the f32 filter only ever *rejects* documents whose f32 score is below
-// Sk·(1-2^-18) where Sk is the exact f64 k-th best so far; the f32 error bound is < 2^-18
-// relative, so no document of the true top-k is ever rejected; everything that
-// survives is ranked by its exact f64 score.
+// Exactness: the f32 filter only ever *rejects* documents whose f32 score is below Sk·(1-2^-18) where Sk is the
+// exact f64 k-th best so far; the f32 error bound is < 2^-18 relative; everything that survives is
+// ranked by its exact f64 score.
 #include <stdlib.h>
 #include <string.h>
 
@@ -30,8 +22,7 @@
 
 #include "bm25x_common.h"
 
-#include "bm25x_search_kernel.cuh"
-#include "bm25x_search_wq.cuh"
+#include "bm25x_device.cuh"
 
 namespace {
 
@@ -106,28 +97,6 @@ struct bm25x_batch {
     void *last_stream = nullptr;
 };
 
-template <class C>
-static int launch_class(const bm25x_index *ix, SearchParams &sp, cudaStream_t stream) {
-    using S = Smem<C>;
-    static bool configured[64] = {false};
-    auto kern = k_search<C>;
-    if (!configured[ix->device & 63]) {
-        BM25X_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::total));
-        configured[ix->device & 63] = true;
-    }
-    int per_sm = 0;
-    BM25X_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C::THREADS, S::total));
-    if (per_sm < 1) {
-        bm25x_set_error("k_search<M=%d> does not fit on an SM (smem %zu)", C::M, (size_t)S::total);
-        return BM25X_ERR_CUDA;
-    }
-    uint32_t grid = (uint32_t)(per_sm * ix->sm_count);
-    if (grid > sp.nq) grid = sp.nq;
-    kern<<<grid, C::THREADS, S::total, stream>>>(sp);
-    BM25X_CUDA_TRY(cudaGetLastError());
-    return BM25X_OK;
-}
-
 // kernel v6 (bm25x_search_ring.cu: warp per query, ring stages + presence map), one entry per pool capacity
 int bm25x_launch_ring_kp64(int device, int sm_count, const SearchParams &sp, int M, cudaStream_t stream);
 int bm25x_launch_ring_kp256(int device, int sm_count, const SearchParams &sp, int M, cudaStream_t stream);
@@ -140,40 +109,6 @@ static int launch_ring_k(const bm25x_index *ix, const SearchParams &sp, int M, c
     if (sp.k <= 1024) return bm25x_launch_ring_kp2048(ix->device, ix->sm_count, sp, M, stream);
     return bm25x_launch_ring_kp131072(ix->device, ix->sm_count, sp, M, stream);  // candidate pools in HBM
 }
-
-// kernel v5 (warp per query): k <= 128 and <= 8 live terms
-template <class C>
-static int launch_wq(const bm25x_index *ix, SearchParams &sp, cudaStream_t stream) {
-    static bool configured[64] = {false};
-    auto kern = k_search_wq<C>;
-    if (!configured[ix->device & 63]) {
-        BM25X_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::total));
-        configured[ix->device & 63] = true;
-    }
-    uint32_t grid = (uint32_t)ix->sm_count;
-    uint32_t need = (sp.nq + C::WARPS - 1) / C::WARPS;
-    if (grid > need) grid = need;
-    kern<<<grid, C::THREADS, C::total, stream>>>(sp);
-    BM25X_CUDA_TRY(cudaGetLastError());
-    return BM25X_OK;
-}
-
-template <int M>
-static int launch_wq_k(const bm25x_index *ix, SearchParams &sp, cudaStream_t stream) {
-    if (sp.k <= 32) return launch_wq<WCfg<M, 128>>(ix, sp, stream);
-    return launch_wq<WCfg<M, 256>>(ix, sp, stream);
-}
-
-// BM25X_KERNEL=cta | wq selects the previous kernel generations (A/B timing, tools/time_variants.py); default: ring
-static int kernel_generation() {
-    static int gen = -1;
-    if (gen < 0) {
-        const char *e = getenv("BM25X_KERNEL");
-        gen = (e && strcmp(e, "cta") == 0) ? 4 : (e && strcmp(e, "wq") == 0) ? 5 : 6;
-    }
-    return gen;
-}
-static bool use_warp_kernel(uint32_t k, int M) { return kernel_generation() == 5 && k <= 128 && M <= 8; }
 
 template <typename T>
 static int batch_alloc(bm25x_batch *b, T **p, size_t n) {
@@ -221,7 +156,7 @@ extern "C" int bm25x_batch_prepare(bm25x_index *ix, uint32_t nq, const uint32_t 
         bm25x_set_error("number of needed rows is set to 0");  // scanners/default.rs:114-116
         return BM25X_ERR_LIMIT_ZERO;
     }
-    if (k > BM25X_MAX_K || (k > 1024 && kernel_generation() != 6)) {
+    if (k > BM25X_MAX_K) {
         bm25x_set_error("bm25x_batch_prepare: k=%u > BM25X_MAX_K=%d", k, BM25X_MAX_K);
         return BM25X_ERR_UNSUPPORTED;
     }
@@ -483,26 +418,7 @@ extern "C" int bm25x_batch_run(bm25x_batch *b, void *stream_v, bm25x_search_stat
         sp.out_n = b->d_out_n;
         BM25X_CUDA_TRY(cudaMemsetAsync(g.d_counter, 0, sizeof(int), st));
         int rc = BM25X_OK;
-        if (kernel_generation() == 6) {
-            rc = launch_ring_k(ix, sp, g.M, st);
-        } else if (use_warp_kernel(b->k, g.M)) {
-            switch (g.M) {
-                case 1: rc = launch_wq_k<1>(ix, sp, st); break;
-                case 2: rc = launch_wq_k<2>(ix, sp, st); break;
-                case 3: rc = launch_wq_k<3>(ix, sp, st); break;
-                case 4: rc = launch_wq_k<4>(ix, sp, st); break;
-                default: rc = launch_wq_k<8>(ix, sp, st); break;
-            }
-        } else
-        switch (g.M) {
-            case 1: rc = launch_class<KCfg<1>>(ix, sp, st); break;
-            case 2: rc = launch_class<KCfg<2>>(ix, sp, st); break;
-            case 3: rc = launch_class<KCfg<3>>(ix, sp, st); break;
-            case 4: rc = launch_class<KCfg<4>>(ix, sp, st); break;
-            case 8: rc = launch_class<KCfg<8>>(ix, sp, st); break;
-            case 16: rc = launch_class<KCfg<16>>(ix, sp, st); break;
-            default: rc = launch_class<KCfg<32>>(ix, sp, st); break;
-        }
+        rc = launch_ring_k(ix, sp, g.M, st);
         if (rc != BM25X_OK) return rc;
         launches++;
     }

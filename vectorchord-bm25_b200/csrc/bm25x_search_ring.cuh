@@ -33,12 +33,15 @@
 // everything else is ranked by (f64 score desc, doc id asc).
 #pragma once
 
-#include "bm25x_search_wq.cuh"
+#include "bm25x_device.cuh"
 
 namespace {
 
 #ifndef BM25X_RING_LOG_R
 #define BM25X_RING_LOG_R -1
+#endif
+#ifndef BM25X_RING_MAPBYTES
+#define BM25X_RING_MAPBYTES 0  // presence map bytes when not a power of two (multiple of 16); 0: 2^BM25X_RING_LOG_S
 #endif
 #ifndef BM25X_RING_LOG_S
 #define BM25X_RING_LOG_S 13
@@ -59,7 +62,7 @@ namespace {
 #define BM25X_RING_SB 1  // 1: single-buffered rings (refill after the chunk, next round prefetched into L2); 0: double-buffered
 #endif
 #ifndef BM25X_RING_SUBT
-#define BM25X_RING_SUBT 640  // classes of 8+ terms: postings per map generation (sub-window) — bounds the false alarms
+#define BM25X_RING_SUBT (1u << 30)  // classes of 8+ terms: postings per map generation (sub-window); default: off (measured: no gain, profiles/README.md)
 #endif
 #ifndef BM25X_RING_ADAPT
 #define BM25X_RING_ADAPT 1  // 1: ring sizes per query ∝ df; 0: M equal rings
@@ -83,10 +86,14 @@ struct RCfg {
     // 2^LOG_RMIN .. 2^LOG_RMAX postings): head terms next to rare ones get wide windows instead of M equal rings of
     // which the rare terms' stay empty; queries with fewer than M terms use the whole budget.
     static constexpr int BUDGET = M_ * R;
+    // Only the classes of 8+ terms size their rings per query (that is where head terms meet rare ones); for 1..4 terms
+    // the geometry stays a compile-time constant (M equal rings): runtime masks and bases cost the 3-term loop 10 %.
+    static constexpr bool ADAPT = (BM25X_RING_ADAPT != 0) && M_ >= 8;
     static constexpr int LOG_RMIN = 6;
     static constexpr int LOG_RMAX = (LOG_R + 2 > 10 ? 10 : LOG_R + 2) > LOG_R ? (LOG_R + 2 > 10 ? 10 : LOG_R + 2) : LOG_R;
     static constexpr int LOG_S = M_ == 1 ? 8 : BM25X_RING_LOG_S;  // presence map bytes = dense accumulator bytes (unused for one term)
-    static constexpr uint32_t ACC_DOCS = (1u << LOG_S) / 4u;
+    static constexpr uint32_t MAP_BYTES = M_ == 1 ? 256u : (BM25X_RING_MAPBYTES ? (uint32_t)BM25X_RING_MAPBYTES : (1u << LOG_S));
+    static constexpr uint32_t ACC_DOCS = MAP_BYTES / 4u;
     static constexpr int U = BM25X_RING_U;          // 16-byte shared loads (2 postings) per lane and trip
     static constexpr int TRIP = 64 * U;             // postings per warp trip
     static constexpr int TMAX = 32 / (2 * U) < 4 ? 32 / (2 * U) : 4;  // trips between two compactions of the detected postings
@@ -98,7 +105,7 @@ struct RCfg {
     static constexpr bool SB = BM25X_RING_SB != 0;
     static constexpr size_t off_ring = 0;
     static constexpr size_t off_map = off_ring + (size_t)M_ * R * sizeof(Posting);
-    static constexpr size_t off_pool_s = off_map + ((size_t)1 << LOG_S);
+    static constexpr size_t off_pool_s = off_map + (size_t)MAP_BYTES;
     static constexpr size_t off_pool_d = off_pool_s + POOL_SMEM * 8;
     static constexpr size_t off_pool_g = off_pool_d + POOL_SMEM * 4;
     static constexpr size_t off_cand = off_pool_g + POOL_SMEM * 4;
@@ -112,12 +119,13 @@ struct RCfg {
     static constexpr size_t total = shared_bytes + warp_bytes * WARPS;
     static constexpr int THREADS = WARPS * 32;
     static_assert(WARPS >= 1, "one warp must fit");
-    static_assert(LOG_RMAX <= 10 && LOG_R >= LOG_RMIN && M_ <= 32 && ((1u << LOG_S) / 4u) <= 32768u,
+    static_assert(LOG_RMAX <= 10 && LOG_R >= LOG_RMIN && M_ <= 32 && MAP_BYTES / 4u <= 32768u && MAP_BYTES % 16u == 0u,
                   "entry format: bit 15 = dense flavour (15-bit doc offset), else 5-bit run | 10-bit ring position");
     static_assert(ACC_DOCS >= 64, "accumulator too small");
 };
 
-__device__ __forceinline__ uint32_t ring_slot(uint32_t doc, int log_s) { return (doc * 0x9E3779B1u) >> (32 - log_s); }
+// slot of a document in a map of `bytes` cells: multiplicative hash, then the high half of hash × bytes (any size)
+__device__ __forceinline__ uint32_t ring_slot(uint32_t doc, uint32_t bytes) { return __umulhi(doc * 0x9E3779B1u, bytes); }
 
 // lower_bound of `doc` in ring positions [a, e) (posting indices of the term; the ring holds index i at i & RM).
 // Fixed LOG_R + 1 power-of-two steps, no data-dependent branch: every lane of a verification pass searches the same run,
@@ -206,7 +214,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
         mbar_fence_init();
     }
     if (C::M > 1)
-        for (int i = lane; i < (1 << C::LOG_S) / 16; i += 32) ((uint4 *)map)[i] = make_uint4(0, 0, 0, 0);
+        for (int i = lane; i < (int)(C::MAP_BYTES / 16u); i += 32) ((uint4 *)map)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
     const uint32_t k = p.k;
     const double kEps = 1.0 / 262144.0;
@@ -245,19 +253,38 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
         bool small_rings = true;  // every ring <= 2^LOG_R postings: searches need LOG_R + 1 steps only
         Posting *myring = rings;
         auto alloc_rings = [&](uint32_t streamed) {
+            if constexpr (!C::ADAPT) {  // M equal rings at fixed places
+                rlog = C::LOG_R;
+                rbase = (uint32_t)(lane < C::M ? lane : 0) * C::R;
+                rsize = C::R;
+                rmask = C::R - 1u;
+                myring = rings + rbase;
+                small_rings = true;
+                return;
+            }
             const bool mine = lane < (int)m && ((streamed >> lane) & 1u);
             unsigned long long sumdf = mine ? dfj : 0u;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) sumdf += __shfl_xor_sync(FULL, sumdf, o);
-            if (!BM25X_RING_ADAPT) sumdf = (unsigned long long)dfj * C::M;  // equal shares
             uint32_t size = 0;
             rlog = 0;
-            if (mine) {
-                const uint32_t share = (uint32_t)(((unsigned long long)C::BUDGET * dfj) / sumdf);
-                rlog = share > 1u ? 31u - (uint32_t)__clz(share) : 0u;
-                rlog = min(max(rlog, (uint32_t)C::LOG_RMIN), (uint32_t)C::LOG_RMAX);
-                while (rlog > (uint32_t)C::LOG_RMIN && (1u << (rlog - 1u)) >= dfpad) rlog--;  // no larger than the list
-                size = 1u << rlog;
+            {
+                // share of the budget, as a power of two: rounded to the NEAREST one when all of these fit, else down
+                uint32_t lo2 = 0, near2 = 0;
+                if (mine) {
+                    const uint32_t share = (uint32_t)(((unsigned long long)C::BUDGET * dfj) / sumdf);
+                    lo2 = share > 1u ? 31u - (uint32_t)__clz(share) : 0u;
+                    near2 = lo2 + ((unsigned long long)share * share >= (2ull << (2u * lo2)) ? 1u : 0u);  // share >= √2·2^lo2
+                    lo2 = min(max(lo2, (uint32_t)C::LOG_RMIN), (uint32_t)C::LOG_RMAX);
+                    near2 = min(max(near2, (uint32_t)C::LOG_RMIN), (uint32_t)C::LOG_RMAX);
+                    while (lo2 > (uint32_t)C::LOG_RMIN && (1u << (lo2 - 1u)) >= dfpad) lo2--;  // no larger than the list
+                    while (near2 > (uint32_t)C::LOG_RMIN && (1u << (near2 - 1u)) >= dfpad) near2--;
+                }
+                const bool fits = __reduce_add_sync(FULL, mine ? 1u << near2 : 0u) <= (uint32_t)C::BUDGET;
+                if (mine) {
+                    rlog = fits ? near2 : lo2;
+                    size = 1u << rlog;
+                }
             }
             uint32_t used = __reduce_add_sync(FULL, size);
             while (used > (uint32_t)C::BUDGET) {  // the minimum sizes of many rare terms can overshoot: halve the largest ring
@@ -272,7 +299,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
             // the rest of the budget: double EVERY ring that can still grow, as long as all of them fit (keeps the
             // proportions: equal terms keep equal rings)
             for (;;) {
-                const bool can = BM25X_RING_ADAPT && mine && rlog < (uint32_t)C::LOG_RMAX && size < dfpad;
+                const bool can = mine && rlog < (uint32_t)C::LOG_RMAX && size < dfpad;
                 const uint32_t extra = __reduce_add_sync(FULL, can ? size : 0u);
                 if (extra == 0u || used + extra > (uint32_t)C::BUDGET) break;
                 if (can) {
@@ -294,6 +321,9 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
             small_rings = __reduce_max_sync(FULL, rlog) <= (uint32_t)C::LOG_R;
         };
         alloc_rings(FULL);
+        // ring geometry of run i (warp-uniform i)
+        auto ring_base = [&](int i) -> uint32_t { return C::ADAPT ? __shfl_sync(FULL, rbase, i) : (uint32_t)i * C::R; };
+        auto ring_mask = [&](int i) -> uint32_t { return C::ADAPT ? __shfl_sync(FULL, rmask, i) : (uint32_t)C::R - 1u; };
         uint32_t rd = 0, wr = 0;  // my run: postings [0, rd) consumed, [rd, wr) in the ring (wr: landed at the next wait)
         uint32_t lo = 0;          // every posting with doc < lo has been consumed
         // MaxScore pruning (warp-uniform): terms in ne_mask are no longer streamed; ub_ne = Σ of their score bounds
@@ -427,7 +457,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                 }
                 if (changed) {
                     refresh_filter();
-                    if (BM25X_RING_ADAPT && C::SB) {
+                    if (C::ADAPT && C::SB) {
                         // the pruned terms' rings go back to the budget: the streamed terms get wider windows.  Their rings
                         // move, so what they held beyond rd is fetched again (a few hundred postings, a few times per query)
                         alloc_rings(~ne_mask);
@@ -497,7 +527,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                     Posting own;
                     own.doc = 0;
                     own.w = 0;
-                    const uint32_t jbase = __shfl_sync(FULL, rbase, j & 31u);
+                    const uint32_t jbase = C::ADAPT ? __shfl_sync(FULL, rbase, j & 31u) : (j & 31u) * C::R;
                     if (has && !by_doc) own = rings[jbase + (ent & 0x3FFu)];
                     const uint32_t doc = by_doc ? lo + (ent & 0x7FFFu) : own.doc;
                     float F = 0.f;
@@ -514,7 +544,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                     };
                     auto filter_term = [&](int i) {
                         const uint32_t ai = __shfl_sync(FULL, rd, i), ei = __shfl_sync(FULL, e, i);
-                        const uint32_t ib = __shfl_sync(FULL, rbase, i), im = __shfl_sync(FULL, rmask, i);
+                        const uint32_t ib = ring_base(i), im = ring_mask(i);
                         const float s0 = __shfl_sync(FULL, s0f, i);
                         uint32_t wi = 0u;
                         if (has && !((ne_mask >> i) & 1u)) {
@@ -607,7 +637,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
 #pragma unroll 1
                             for (int i = 0; i < (int)m; ++i) {
                                 const uint32_t ai = __shfl_sync(FULL, rd, i), ei = __shfl_sync(FULL, e, i);
-                                const uint32_t ib = __shfl_sync(FULL, rbase, i), im = __shfl_sync(FULL, rmask, i);
+                                const uint32_t ib = ring_base(i), im = ring_mask(i);
                                 uint32_t wi = 0u;
                                 if (keep && !((ne_mask >> i) & 1u)) wi = holder(i, ib, im, ai, ei);
                                 exact_term(i, wi);
@@ -675,8 +705,8 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                     td &= td - 1u;
                     const uint32_t a = __shfl_sync(FULL, rd, j), ee = __shfl_sync(FULL, e, j);
                     const float s0 = __shfl_sync(FULL, s0f, j);
-                    const Posting *rgp = rings + __shfl_sync(FULL, rbase, j);
-                    const uint32_t jm = __shfl_sync(FULL, rmask, j);
+                    const Posting *rgp = rings + ring_base(j);
+                    const uint32_t jm = ring_mask(j);
                     for (uint32_t i = a + lane; i < ee; i += 32) {
                         const Posting v = rgp[i & jm];
                         acc[v.doc - lo] += score_f32(v.w, s0, s1f);
@@ -711,7 +741,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                                 const bool valid = !CHECK || ix[u] + h - ra < rnj;  // unsigned: also false below ra
                                 bool c = false;
                                 if (TEST || MARK) {
-                                    const uint32_t slot = ring_slot(doc, C::LOG_S);
+                                    const uint32_t slot = ring_slot(doc, C::MAP_BYTES);
                                     if (TEST) c = map[slot] == genv;
                                     if (MARK && valid) map[slot] = (uint8_t)genv;
                                 }
@@ -755,8 +785,8 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                             wl = __shfl_sync(FULL, wlim, rj);
                             tw = __shfl_sync(FULL, tiew, rj);
                             rnj = ree - ra;
-                            rg = (const uint4 *)(rings + __shfl_sync(FULL, rbase, rj));
-                            rm = __shfl_sync(FULL, rmask, rj);
+                            rg = (const uint4 *)(rings + ring_base(rj));
+                            rm = ring_mask(rj);
                             tdk = f.tie_dk;  // snapshot with tw: a stale (looser) pair stays valid, thresholds only tighten
                             pb = ra & ~1u;
                             variant = __shfl_sync(FULL, myvariant, rj);
