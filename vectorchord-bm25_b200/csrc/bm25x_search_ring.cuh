@@ -40,6 +40,10 @@ namespace {
 #ifndef BM25X_RING_LOG_R
 #define BM25X_RING_LOG_R -1
 #endif
+#ifndef BM25X_RING_BITMAP
+#define BM25X_RING_BITMAP 0  // 1: the presence map is a BIT map (one bit per cell, marks by shared-memory atomicOr, cleared
+                             // per window) — 8x the cells of the byte map in the same memory; 0: byte map with generation tags
+#endif
 #ifndef BM25X_RING_MAPBYTES
 #define BM25X_RING_MAPBYTES 0  // presence map bytes when not a power of two (multiple of 16); 0: 2^BM25X_RING_LOG_S
 #endif
@@ -96,7 +100,8 @@ struct RCfg {
     static constexpr uint32_t ACC_DOCS = MAP_BYTES / 4u;
     static constexpr int U = BM25X_RING_U;          // 16-byte shared loads (2 postings) per lane and trip
     static constexpr int TRIP = 64 * U;             // postings per warp trip
-    static constexpr int TMAX = 32 / (2 * U) < 4 ? 32 / (2 * U) : 4;  // trips between two compactions of the detected postings
+    static constexpr int TMAX = 32 / (2 * U) < 3 ? 32 / (2 * U) : 3;  // trips between two compactions of the detected postings
+                                                                      // (3: the list stays small enough for a 14th warp per SM)
     static constexpr int LCAP = TMAX * TRIP + 64;   // candidate list entries, 16 bits each (verified when > 64 are listed)
     static constexpr int INIT = BM25X_RING_INIT;    // postings per run in the very first load (a threshold exists early)
     // Single-buffered: the whole ring is one window; it is refilled AFTER the chunk (the load is exposed, but it comes
@@ -691,6 +696,10 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                 multi = C::M > 1 && __popc(todo) > 1;
                 if (multi) gen = gen % 255u + 1u;
                 genv = gen;
+                if (BM25X_RING_BITMAP && multi) {  // bit cells carry no generation: clear the map for this window
+                    for (int i = lane; i < (int)(C::MAP_BYTES / 16u); i += 32) ((uint4 *)map)[i] = make_uint4(0, 0, 0, 0);
+                    __syncwarp();
+                }
                 // wlim == ~0: no single-term posting of the run can pass → the loop variant without that test; the first
                 // non-empty run has nothing to test against, the last one nobody to mark for
                 myvariant = (wlim != 0xFFFFFFFFu ? 4 : 0) | (multi && lane != __ffs(todo) - 1 ? 2 : 0) |
@@ -741,9 +750,16 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                                 const bool valid = !CHECK || ix[u] + h - ra < rnj;  // unsigned: also false below ra
                                 bool c = false;
                                 if (TEST || MARK) {
+#if BM25X_RING_BITMAP
+                                    const uint32_t slot = ring_slot(doc, C::MAP_BYTES * 8u);
+                                    uint32_t *cell = (uint32_t *)map + (slot >> 5);
+                                    if (TEST) c = (*cell >> (slot & 31u)) & 1u;
+                                    if (MARK && valid) atomicOr(cell, 1u << (slot & 31u));
+#else
                                     const uint32_t slot = ring_slot(doc, C::MAP_BYTES);
                                     if (TEST) c = map[slot] == genv;
                                     if (MARK && valid) map[slot] = (uint8_t)genv;
+#endif
                                 }
                                 if (SOLO) c = c | ((w > wl) & !((w == tw) & (doc > tdk)));  // bitwise: no branches
                                 bits |= (uint32_t)(valid & c) << (2 * u + h);
