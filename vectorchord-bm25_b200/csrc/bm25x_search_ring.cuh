@@ -41,14 +41,14 @@ namespace {
 #define BM25X_RING_LOG_R -1
 #endif
 #ifndef BM25X_RING_BITMAP
-#define BM25X_RING_BITMAP 0  // 1: the presence map is a BIT map (one bit per cell, marks by shared-memory atomicOr, cleared
+#define BM25X_RING_BITMAP 1  // 1: the presence map is a BIT map (one bit per cell, marks by shared-memory atomicOr, cleared
                              // per window) — 8x the cells of the byte map in the same memory; 0: byte map with generation tags
 #endif
 #ifndef BM25X_RING_MAPBYTES
 #define BM25X_RING_MAPBYTES 0  // presence map bytes when not a power of two (multiple of 16); 0: 2^BM25X_RING_LOG_S
 #endif
 #ifndef BM25X_RING_LOG_S
-#define BM25X_RING_LOG_S 13
+#define BM25X_RING_LOG_S -1  // log2 of the map bytes; -1: per class (2 KiB of bit cells up to 4 terms, 8 KiB beyond)
 #endif
 #ifndef BM25X_RING_U
 #define BM25X_RING_U 2
@@ -95,7 +95,7 @@ struct RCfg {
     static constexpr bool ADAPT = (BM25X_RING_ADAPT != 0) && M_ >= 8;
     static constexpr int LOG_RMIN = 6;
     static constexpr int LOG_RMAX = (LOG_R + 2 > 10 ? 10 : LOG_R + 2) > LOG_R ? (LOG_R + 2 > 10 ? 10 : LOG_R + 2) : LOG_R;
-    static constexpr int LOG_S = M_ == 1 ? 8 : BM25X_RING_LOG_S;  // presence map bytes = dense accumulator bytes (unused for one term)
+    static constexpr int LOG_S = M_ == 1 ? 8 : (BM25X_RING_LOG_S > 0 ? BM25X_RING_LOG_S : (BM25X_RING_BITMAP && M_ <= 4 ? 11 : 13));  // presence map bytes = dense accumulator bytes (unused for one term)
     static constexpr uint32_t MAP_BYTES = M_ == 1 ? 256u : (BM25X_RING_MAPBYTES ? (uint32_t)BM25X_RING_MAPBYTES : (1u << LOG_S));
     static constexpr uint32_t ACC_DOCS = MAP_BYTES / 4u;
     static constexpr int U = BM25X_RING_U;          // 16-byte shared loads (2 postings) per lane and trip
