@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-2 GPU pass g: secondary workloads at size (C4 pruned 100k / exhaustive 4k, C2, C5 on one GPU).
 mkdir -p gpurun_out
-O=gpurun_out/r2g
+O=gpurun_out/r2p
 timeout 400 python bench.py --workload c4 --queries 100000 --steps 3 --warmup 1 > ${O}_bench_c4_pruned_100k.json 2> ${O}_bench_c4_pruned_100k.err; echo "c4 pruned rc=$?"
 timeout 400 python bench.py --workload c4 --queries 4000 --no-prune --no-cpu-baseline --steps 2 --warmup 1 > ${O}_bench_c4_exhaustive_4k.json 2> ${O}_bench_c4_exhaustive_4k.err; echo "c4 exhaustive rc=$?"
 timeout 200 python bench.py --workload c2 --steps 10 --warmup 3 > ${O}_bench_c2.json 2> ${O}_bench_c2.err; echo "c2 rc=$?"
