@@ -688,7 +688,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
             // memory; docs are distinct inside a run: plain read-modify-write, __syncwarp between runs), then scanned.
             uint32_t todo = 0u, ra = 0u, ree = 0u, rnj = 0u, wl = 0u, tw = 0u, tdk = 0u, pb = 0u, genv = 0u, dbase = 0u, rm = 1u;
             int rj = -1, variant = 0;
-            bool first = true, multi = false;
+            bool multi = false;
             const uint4 *rg = nullptr;
             int myvariant = 0;  // lane j: loop variant of run j in this window (4: single-term test, 2: test, 1: mark)
             if (!dense) {
@@ -783,44 +783,44 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                     nc += __popc(bal);
                 }
             };
-            bool finished = false;
-            while (!finished) {
+            // Producer loop: runs (or the accumulator scan) list candidates until the list wants to be verified or the
+            // window is done; ONE verification site after it.
+            bool more = true;
+            while (more) {
                 if (!dense) {
-                    if (pb >= ree) {  // next run
-                        if (rj >= 0) {
-                            first = false;
-                            __syncwarp();  // this run's marks are visible to the next run's tests
-                        }
-                        if (!todo) {
-                            finished = true;
-                        } else {
+                    for (;;) {
+                        if (pb >= ree) {  // next run
+                            if (rj >= 0) __syncwarp();  // this run's marks are visible to the next run's tests
+                            if (!todo) {
+                                more = false;
+                                break;
+                            }
                             rj = __ffs(todo) - 1;
                             todo &= todo - 1u;
                             ra = __shfl_sync(FULL, rd, rj);
                             ree = __shfl_sync(FULL, e, rj);
                             wl = __shfl_sync(FULL, wlim, rj);
                             tw = __shfl_sync(FULL, tiew, rj);
+                            variant = __shfl_sync(FULL, myvariant, rj);
                             rnj = ree - ra;
                             rg = (const uint4 *)(rings + ring_base(rj));
                             rm = ring_mask(rj);
                             tdk = f.tie_dk;  // snapshot with tw: a stale (looser) pair stays valid, thresholds only tighten
                             pb = ra & ~1u;
-                            variant = __shfl_sync(FULL, myvariant, rj);
-                            if (variant == 0) pb = ree;  // nothing to learn from this run in this window
                         }
-                    }
-                    if (!finished && pb < ree) {
                         switch (variant) {
+                            case 0: pb = ree; break;  // nothing to learn from this run in this window
+                            case 3: run(std::true_type(), std::true_type(), std::false_type()); break;
                             case 1: run(std::false_type(), std::true_type(), std::false_type()); break;
                             case 2: run(std::true_type(), std::false_type(), std::false_type()); break;
-                            case 3: run(std::true_type(), std::true_type(), std::false_type()); break;
                             case 4: run(std::false_type(), std::false_type(), std::true_type()); break;
                             case 5: run(std::false_type(), std::true_type(), std::true_type()); break;
                             case 6: run(std::true_type(), std::false_type(), std::true_type()); break;
                             default: run(std::true_type(), std::true_type(), std::true_type()); break;
                         }
-                        __syncwarp();  // the listed entries are visible to every lane
+                        if (nc > 64u) break;
                     }
+                    __syncwarp();  // the listed entries are visible to every lane
                 } else {
                     const float *acc = (const float *)map;
                     while (dbase < span && nc <= 64u) {
@@ -833,9 +833,9 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                         dbase += 32;
                     }
                     __syncwarp();
-                    finished = dbase >= span;
+                    more = dbase < span;
                 }
-                if (nc > 64u || (finished && nc)) verify();
+                if (nc) verify();
             }
             rd = e;
             }  // sub-windows
