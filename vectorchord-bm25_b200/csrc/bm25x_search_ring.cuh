@@ -485,10 +485,17 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
             uint32_t hi = __reduce_min_sync(FULL, limit);
             bool last = hi == INF;
             uint32_t e = rd;
-            if (act) {
-                if (last) e = avail_e;
-                else if (small_rings) e = ring_lower_bound<C, C::LOG_R>(myring, rmask, rd, avail_e, hi);
-                else e = ring_lower_bound<C>(myring, rmask, rd, avail_e, hi);
+            {
+                // a window usually ends in the last few postings of every ring (all runs advance together): when the posting
+                // 32 before the end is still inside the window for every run, 6 search steps over that tail are enough
+                const bool tail = act && !last && avail_e - rd > 32u && myring[(avail_e - 33u) & rmask].doc < hi;
+                if (__all_sync(FULL, tail || !act || last)) {
+                    if (act) e = last ? avail_e : ring_lower_bound<C, 5>(myring, rmask, avail_e - 32u, avail_e, hi);
+                } else if (act) {
+                    if (last) e = avail_e;
+                    else if (small_rings) e = ring_lower_bound<C, C::LOG_R>(myring, rmask, rd, avail_e, hi);
+                    else e = ring_lower_bound<C>(myring, rmask, rd, avail_e, hi);
+                }
             }
             // ---- dense or sparse?  (expected number of documents held by two runs in this window) ----
             bool dense = false;
@@ -524,9 +531,14 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
             uint32_t nc = 0;  // listed candidates (warp-uniform)
             // ---- verification: 32 listed postings at a time ----
             auto verify = [&]() {
-                for (uint32_t base = 0; base < nc; base += 32) {
-                    const bool has = base + lane < nc;
-                    const uint32_t ent = has ? cand[base + lane] : 0u;
+                // Three streamed runs (the headline class): TWO lanes per listed posting, each searches one of the two
+                // other runs — one search per pass instead of two in a row; the even lane of a pair carries the candidate.
+                const bool pairs = C::M == 3 && !C::ADAPT && !dense && m == 3u && ne_mask == 0u;
+                const uint32_t per_pass = pairs ? 16u : 32u;
+                for (uint32_t base = 0; base < nc; base += per_pass) {
+                    const uint32_t ci = base + (pairs ? (uint32_t)lane >> 1 : (uint32_t)lane);
+                    bool has = ci < nc;
+                    const uint32_t ent = has ? cand[ci] : 0u;
                     const bool by_doc = (ent >> 15) != 0u;            // dense flavour: document given as offset from lo
                     const uint32_t j = by_doc ? 32u : (ent >> 10) & 31u;
                     Posting own;
@@ -563,7 +575,30 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                         }
                         return wi;
                     };
-                    if constexpr (KEEPW) {
+                    if (C::M == 3 && pairs) {
+                        if constexpr (C::M == 3) {
+                            // my run to search: the first (even lane) or second (odd lane) of the two runs other than j
+                            const uint32_t o = (lane & 1) ? (j == 2u ? 1u : 2u) : (j == 0u ? 1u : 0u);
+                            const uint32_t ao = __shfl_sync(FULL, rd, o), eo = __shfl_sync(FULL, e, o);
+                            uint32_t wo = 0u;
+                            if (has) wo = ring_find<C, C::LOG_R>(rings + o * C::R, C::R - 1u, ao, eo, doc);
+                            const uint32_t wx = __shfl_xor_sync(FULL, wo, 1);  // the partner's run
+                            const uint32_t ox = (lane & 1) ? (j == 0u ? 1u : 0u) : (j == 2u ? 1u : 2u);
+                            has = has && !(lane & 1);
+#pragma unroll
+                            for (int i = 0; i < 3; ++i) {
+                                const float s0 = __shfl_sync(FULL, s0f, i);
+                                const uint32_t wi = (uint32_t)i == j ? own.w : ((uint32_t)i == o ? wo : ((uint32_t)i == ox ? wx : 0u));
+                                if (has && wi) {
+                                    F += score_f32(wi, s0, s1f);
+                                    cnt++;
+                                    sig = make_sig(i, wi);
+                                    later |= (uint32_t)i > j;
+                                }
+                                wv[i] = has ? wi : 0u;
+                            }
+                        }
+                    } else if constexpr (KEEPW) {
 #pragma unroll
                         for (int i = 0; i < C::M; ++i)
                             if (i < (int)m) wv[i] = filter_term(i);
