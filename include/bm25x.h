@@ -30,7 +30,7 @@ extern "C" {
 #define BM25X_ERR_LIMIT_ZERO 5  /* k == 0: "number of needed rows is set to 0" (scanners/default.rs:114-116) */
 
 #define BM25X_MAX_K 65535 /* the reference's bm25.limit maximum (src/index/gucs.rs:37-46) */
-#define BM25X_MAX_QUERY_TERMS 32
+#define BM25X_MAX_QUERY_TERMS 64 /* live (known, distinct) tokens per query; more than 32 run as two passes over term groups */
 #define BM25X_TERM_MISSING 0xFFFFFFFFu
 #define BM25X_KEY_WIDTH 16 /* crates/bm25/src/lib.rs:37 WIDTH */
 

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.environ.get("BM25X_LIBRARY") or os.path.join(_HERE, "libbm25x.so")
 
 MAX_K = 65535
-MAX_QUERY_TERMS = 32
+MAX_QUERY_TERMS = 64
 TERM_MISSING = 0xFFFFFFFF
 
 

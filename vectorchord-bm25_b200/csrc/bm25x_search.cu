@@ -69,8 +69,8 @@ __global__ void k_evaluate(uint32_t n_pairs, const uint32_t *__restrict__ d_off,
 // Host side
 // =============================================================================================
 
-static const int kClasses[] = {1, 2, 3, 4, 8, 16, 32};
-static const int kNumClasses = 7;
+static const int kClasses[] = {1, 2, 3, 4, 8, 16, 32, 64};  // 64: two passes of the 32-term kernel (33..64 live terms)
+static const int kNumClasses = 8;
 
 struct Group {
     int M = 0;
@@ -189,6 +189,18 @@ extern "C" int bm25x_batch_prepare(bm25x_index *ix, uint32_t nq, const uint32_t 
         uint64_t cst = 0;
         for (uint32_t j = 0; j < m; ++j) cst += h_df[dst[j]];
         cost[i] = cst;
+        if (m > 32 && m <= BM25X_MAX_QUERY_TERMS) {
+            // two-pass query: the 32 rarest terms first (group 0, streamed by the first pass), the others after them;
+            // both groups ascending — the kernel merges them back into ascending term order for the exact sum
+            uint32_t tmp[BM25X_MAX_QUERY_TERMS];
+            std::copy(dst, dst + m, tmp);
+            std::nth_element(tmp, tmp + 32, tmp + m, [&](uint32_t a, uint32_t b) {
+                return h_df[a] != h_df[b] ? h_df[a] < h_df[b] : a < b;
+            });
+            std::sort(tmp, tmp + 32);
+            std::sort(tmp + 32, tmp + m);
+            std::copy(tmp, tmp + m, dst);
+        }
         if (m > BM25X_MAX_QUERY_TERMS) {
 #pragma omp critical
             { bad_query = (int)i; bad_kind = 2; }

@@ -233,8 +233,37 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
         qi = __shfl_sync(FULL, qi, 0);
         if (qi >= (int)p.nq) break;
         const uint32_t qid = p.q_ids[qi];
-        const uint32_t t0 = p.q_off[qi];
-        const uint32_t m = p.q_off[qi + 1] - t0;
+        const uint32_t t0q = p.q_off[qi];
+        const uint32_t m_total = p.q_off[qi + 1] - t0q;
+        // More than 32 terms (lane j = term j holds 32): TWO passes over term groups — the host puts the 32 rarest terms
+        // first.  Pass 0 streams group 0 and probes group 1 for its candidates; pass 1 streams group 1 and owns exactly the
+        // documents that hold no group-0 term.  Every document is emitted once, with its full score; pool and threshold
+        // span the passes.
+        const bool mp = C::M == 32 && m_total > 32u;
+        unsigned long long fetched = 0;
+        uint32_t probe_steps = 0;
+        // per-query pool / threshold state (warp-uniform registers)
+        int pn = 0;
+        WFilter f;
+        f.tv = false;
+        f.Flo = -1.f;
+        f.Sk = 0.0;
+        f.dk = INF;
+        f.tie_sig = SIG_NONE;
+        f.tie_dk = INF;
+        f.ctf = 0.f;
+        for (int pass = 0; pass < (mp ? 2 : 1); ++pass) {
+        const uint32_t t0 = t0q + (pass ? 32u : 0u);
+        const uint32_t m = mp ? (pass ? m_total - 32u : 32u) : m_total;
+        const uint32_t obase = t0q + (pass ? 0u : 32u);          // the other group (probed, never streamed in this pass)
+        const uint32_t on = mp ? (pass ? 32u : m_total - 32u) : (m_total & 0u);  // (& 0: keeps "on" a runtime zero)
+        double ub_oth = 0.0;  // pass 0: Σ score bounds of the other group's terms (they can add to any candidate)
+        if (mp && pass == 0) {
+            double ub = lane < (int)on ? p.ubd[p.q_terms[obase + lane]] : 0.0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ub += __shfl_xor_sync(FULL, ub, o);
+            ub_oth = ub * (1.0 + 1.0e-12);
+        }
         // ---- query terms: lane j < m (TokenTuple of term j: df, postings, score constants) ----
         uint32_t dfj = 0, dfpad = 0, nbj = 0;
         uint64_t pbase = 0, bbase = 0;
@@ -338,26 +367,14 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
         int n_ne = 0;
         float ne_prefix_f = 0.f;   // lane t: Σ bounds of the terms pruned before the t-th one, rounded up
         float FloT = -1.f;         // filter threshold on the score over ALL terms (f.Flo: over the streamed terms only)
-        uint32_t probe_steps = 0;
         bool thr_new = false;     // the threshold moved since the pruned set was last reconsidered
-        unsigned long long fetched = 0;
-        // per-query pool / threshold state (warp-uniform registers)
-        int pn = 0;
-        WFilter f;
-        f.tv = false;
-        f.Flo = -1.f;
-        f.Sk = 0.0;
-        f.dk = INF;
-        f.tie_sig = SIG_NONE;
-        f.tie_dk = INF;
-        f.ctf = 0.f;
         uint32_t wlim = 255u;         // lane j: single-term postings of run j can pass only if w > wlim  (tf >= 1: all)
         uint32_t tiew = 0xFFFFFFFFu;  // lane j: posting word of the tie signature when it belongs to run j
 
         // f32 filter constants from (Sk, tie signature, pruned set)
         auto refresh_filter = [&]() {
-            f.tie_dk = (f.tie_sig != SIG_NONE && ne_mask == 0u) ? f.dk : INF;  // pruned terms: no tie shortcut
-            const double flo = f.Sk * (1.0 - kEps) - ub_ne;
+            f.tie_dk = (f.tie_sig != SIG_NONE && ne_mask == 0u && !mp) ? f.dk : INF;  // pruned / probed terms: no tie shortcut
+            const double flo = f.Sk * (1.0 - kEps) - ub_ne - ub_oth;
             f.Flo = __double2float_rd(flo);
             FloT = __double2float_rd(f.Sk * (1.0 - kEps));
             // F = s0·tf/(tf+s1) >= flo  ⇔  tf >= flo/(s0-flo)·s1  (s0 > flo), never when s0 <= flo.  Solved in f64
@@ -391,6 +408,11 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                 refresh_filter();
             }
         };
+
+        if (pass && f.tv) {  // second pass: the threshold of the first one, solved for this group's terms
+            thr_new = true;
+            refresh_filter();
+        }
 
         // one refill round: lane j appends n postings (even) to its ring
         auto issue_round = [&](uint32_t n) -> bool {
@@ -674,13 +696,43 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                                     }
                             }
                         } else {
+                            // posting word of `doc` in a term that is no lane of this pass (two-pass queries)
+                            auto probe_term = [&](uint32_t term) -> uint32_t {
+                                const uint32_t dft = p.df[term];
+                                const uint32_t l = probe_block(p, p.blk_off[term], (dft + BM25X_BLOCK - 1) / BM25X_BLOCK, doc, probe_steps);
+                                return l > 0u ? probe_in_block(p, p.post_off[term], dft, l - 1u, doc, probe_steps) : 0u;
+                            };
+                            if (mp && pass == 1) {  // documents holding a first-group term were emitted by the first pass
+                                for (uint32_t u = 0; u < on && __any_sync(FULL, keep); ++u) {
+                                    const uint32_t term = p.q_terms[obase + u];
+                                    if (keep && probe_term(term)) keep = false;
+                                }
+                            }
+                            // both groups merged in ascending term id: the reference order of the f64 sum
+                            uint32_t ia = 0, iob = 0;
 #pragma unroll 1
-                            for (int i = 0; i < (int)m; ++i) {
-                                const uint32_t ai = __shfl_sync(FULL, rd, i), ei = __shfl_sync(FULL, e, i);
-                                const uint32_t ib = ring_base(i), im = ring_mask(i);
-                                uint32_t wi = 0u;
-                                if (keep && !((ne_mask >> i) & 1u)) wi = holder(i, ib, im, ai, ei);
-                                exact_term(i, wi);
+                            while (ia < m || iob < on) {
+                                const uint32_t ta = ia < m ? p.q_terms[t0 + ia] : INF, tb = iob < on ? p.q_terms[obase + iob] : INF;
+                                if (ta < tb) {
+                                    const int i = (int)ia;
+                                    const uint32_t ai = __shfl_sync(FULL, rd, i), ei = __shfl_sync(FULL, e, i);
+                                    const uint32_t ib = ring_base(i), im = ring_mask(i);
+                                    uint32_t wi = 0u;
+                                    if (keep && !((ne_mask >> i) & 1u)) wi = holder(i, ib, im, ai, ei);
+                                    exact_term(i, wi);
+                                    ia++;
+                                } else {
+                                    if (pass == 0) {  // first pass: the second group's terms are probed for the survivors
+                                        const double s0 = p.s0d[tb];
+                                        uint32_t wi = 0u;
+                                        if (keep) wi = probe_term(tb);
+                                        if (keep && wi) {
+                                            Sx = __dadd_rn(Sx, score_f64(wi, s0, p.s1d));
+                                            cnt_all++;
+                                        }
+                                    }
+                                    iob++;
+                                }
                             }
                         }
                         keep = keep && (!f.tv || Sx > f.Sk || (Sx == f.Sk && doc < f.dk));
@@ -699,6 +751,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                         if (pn > C::KP - 32 || (!lazy && pn >= (int)k + 32)) pool_cut();
                     }
                 }
+                __syncwarp();  // every lane has read its entries before the producers refill the list
                 nc = 0;
             };
 
@@ -889,8 +942,9 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                 }
             }
         }
-        // ---- Results::into_sorted_vec (search.rs:281) ----
+        // ---- Results::into_sorted_vec (search.rs:281) (after the last pass; between passes: a tidy pool and threshold) ----
         if (pn > 0) pool_cut();
+        }  // passes
         const size_t obase = (size_t)qid * k;
         for (uint32_t i = lane; i < k; i += 32) {
             uint32_t d = INF;
