@@ -275,6 +275,8 @@ def main():
         if rank == 0:
             reference_arm(a, wl, k, cores, cores_how)
         return  # the reference arm runs on rank 0 only; it never loads the product library
+    if world > 1:  # the ranks of one box share its cores: each takes its share for the host side of the C ABI
+        os.environ.setdefault("BM25X_HOST_THREADS", str(max(1, cores // world)))
     import _pkg
     m = _pkg.load()
     m.load_library()

@@ -29,6 +29,10 @@ extern "C" const char *bm25x_last_error(void) { return g_err; }
 
 int bm25x_host_threads(int cap) {
     static const int granted = [] {
+        if (const char *e = getenv("BM25X_HOST_THREADS")) {  // explicit share, e.g. cores / ranks when several ranks share a box
+            const int v = atoi(e);
+            if (v >= 1) return v;
+        }
         int n = omp_get_num_procs();  // honours the affinity mask
         FILE *f = fopen("/sys/fs/cgroup/cpu.max", "r");
         if (f) {
