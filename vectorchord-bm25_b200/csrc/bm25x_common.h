@@ -12,6 +12,9 @@
 
 #define BM25X_BLOCK 128u            // postings per block, as the reference (crates/bm25/src/flush.rs:84)
 #define BM25X_DOC_INF 0xFFFFFFFFu   // exhausted-cursor sentinel, as search.rs:484-496
+#define BM25X_POST_ALIGN 4u         // every term's posting list starts on a multiple of 4 postings: 16-byte TMA granularity of
+                                    // the doc-id-only copy (pdoc, 4 B per posting) as well as of the 8-byte postings
+#define BM25X_POST_SLACK 4u         // slack slots behind the last list, reading as exhausted cursors
 
 void bm25x_set_error(const char *fmt, ...);
 // Host threads this process may really use: the affinity mask capped by the cgroup CPU quota (omp_get_max_threads()
@@ -40,10 +43,12 @@ struct Posting {
 struct DeviceIndex {
     uint32_t n_docs = 0, n_terms = 0;
     uint64_t n_post = 0;      // real postings
-    uint64_t n_post_pad = 0;  // incl. one pad slot per odd-length term (16-byte TMA granularity)
+    uint64_t n_post_pad = 0;  // incl. the pad slots that round every term up to BM25X_POST_ALIGN postings
     uint64_t n_blocks = 0;
     Posting *post = nullptr;        // [n_post_pad] term-major, doc-ascending inside a term
-    uint64_t *post_off = nullptr;   // [n_terms+1] padded offsets (even)
+    uint32_t *pdoc = nullptr;       // [n_post_pad] the doc ids of `post` alone (derived on the device, not replicated): what the
+                                    // 2..4-term classes of k_search_ring stream — their hot loop never reads tf / fieldnorm
+    uint64_t *post_off = nullptr;   // [n_terms+1] padded offsets (multiples of BM25X_POST_ALIGN)
     uint32_t *df = nullptr;         // [n_terms] TokenTuple.number_of_documents
     uint64_t *blk_off = nullptr;    // [n_terms+1] first block index of each term
     uint2 *blk = nullptr;           // [n_blocks] (first doc, last doc) — SummaryTuple.{min,max}_document_id

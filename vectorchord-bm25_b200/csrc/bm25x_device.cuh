@@ -7,6 +7,7 @@
 // One launch = the queries of one term-count class (shared by the translation units of the library).
 struct SearchParams {
     const Posting *post;
+    const uint32_t *pdoc;               // doc ids of `post` alone, same offsets (RCfg::DOCRING classes stream these)
     const uint64_t *post_off;
     const uint32_t *df;
     const uint64_t *blk_off;

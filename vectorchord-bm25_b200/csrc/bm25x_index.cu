@@ -129,12 +129,18 @@ __global__ void k_pad_slots(const uint64_t *__restrict__ off_pad, const uint32_t
                             Posting *__restrict__ post) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_terms) return;
-    if (df[t] & 1u) {
-        Posting p;
-        p.doc = BM25X_DOC_INF;
-        p.w = 0;
-        post[off_pad[t] + df[t]] = p;
-    }
+    Posting p;
+    p.doc = BM25X_DOC_INF;
+    p.w = 0;
+    const uint32_t end = (df[t] + BM25X_POST_ALIGN - 1u) & ~(BM25X_POST_ALIGN - 1u);
+    for (uint32_t i = df[t]; i < end; i++) post[off_pad[t] + i] = p;
+}
+
+// pdoc[i] = post[i].doc: the doc-id-only copy streamed by the 2..4-term classes of k_search_ring (bm25x_search_ring.cuh,
+// RCfg::DOCRING).  Derived data: built here for every way an index comes to life (postings, stored blocks, replica).
+__global__ void k_extract_docs(const Posting *__restrict__ post, uint64_t n, uint32_t *__restrict__ pdoc) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) pdoc[i] = post[i].doc;
 }
 
 // Per 128-posting block: (first doc, last doc) = SummaryTuple.{min,max}_document_id, and the block's score bound =
@@ -347,7 +353,7 @@ static int index_begin(const BuildMeta &m, int device, bm25x_index **ixp) {
         ix->h_df[t] = (uint32_t)n;
         h_off_pad[t] = pp;
         h_blk_off[t] = nb;
-        pp += (n + 1) & ~(uint64_t)1;
+        pp += (n + BM25X_POST_ALIGN - 1) & ~(uint64_t)(BM25X_POST_ALIGN - 1);
         nb += (n + BM25X_BLOCK - 1) / BM25X_BLOCK;
         const double n_stat = m.stat_df ? (double)m.stat_df[t] : (double)n, N_stat = m.stat_df ? (double)m.stat_n_docs : (double)N;
         double idf = log((N_stat + 1.0) / (n_stat + 0.5));
@@ -380,7 +386,8 @@ static int index_begin(const BuildMeta &m, int device, bm25x_index **ixp) {
     d.n_post = P;
     d.n_post_pad = pp;
     d.n_blocks = nb;
-    TRY(dev_alloc(ix, &d.post, pp + 2));
+    TRY(dev_alloc(ix, &d.post, pp + BM25X_POST_SLACK));
+    TRY(dev_alloc(ix, &d.pdoc, pp + BM25X_POST_SLACK));
     TRY(dev_alloc(ix, &d.post_off, (size_t)T + 1));
     TRY(dev_alloc(ix, &d.df, T));
     TRY(dev_alloc(ix, &d.blk_off, (size_t)T + 1));
@@ -393,7 +400,7 @@ static int index_begin(const BuildMeta &m, int device, bm25x_index **ixp) {
     TRY(dev_alloc(ix, &d.ubd, T));
     TRY(dev_alloc(ix, &d.fieldnorm, N));
     TRY(dev_alloc(ix, &d.payload, (size_t)N * 3));
-    CU(cudaMemset((void *)(d.post + pp), 0xFF, 2 * sizeof(Posting)));  // the two slack slots read as exhausted cursors
+    CU(cudaMemset((void *)(d.post + pp), 0xFF, BM25X_POST_SLACK * sizeof(Posting)));  // the slack slots read as exhausted cursors
     CU(cudaMemcpy(d.post_off, h_off_pad.data(), sizeof(uint64_t) * (T + 1), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(d.blk_off, h_blk_off.data(), sizeof(uint64_t) * (T + 1), cudaMemcpyHostToDevice));
     if (T) {
@@ -429,6 +436,10 @@ static cudaError_t index_finish_device(bm25x_index *ix) {
     cudaError_t e = cudaSuccess;
     if (T) {
         k_pad_slots<<<(T + 255) / 256, 256>>>(d.post_off, d.df, T, d.post);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) {
+        k_extract_docs<<<148 * 8, 256>>>(d.post, d.n_post_pad + BM25X_POST_SLACK, d.pdoc);
         e = cudaGetLastError();
     }
     if (e == cudaSuccess && nb) {
@@ -818,7 +829,7 @@ static void layout_arrays(const bm25x_index *ix, void **ptr, uint64_t *bytes) {
     const uint64_t T = d.n_terms, N = d.n_docs;
     void *p[BM25X_N_ARRAYS] = {d.post, d.post_off, d.df, d.blk_off, d.blk, d.s0f, d.s0d, d.s1d, d.s1f, d.fieldnorm, d.payload,
                                d.ubd, d.blk_ub};
-    uint64_t b[BM25X_N_ARRAYS] = {sizeof(Posting) * (d.n_post_pad + 2), 8 * (T + 1), 4 * (T ? T : 1), 8 * (T + 1),
+    uint64_t b[BM25X_N_ARRAYS] = {sizeof(Posting) * (d.n_post_pad + BM25X_POST_SLACK), 8 * (T + 1), 4 * (T ? T : 1), 8 * (T + 1),
                                   8 * (d.n_blocks ? d.n_blocks : 1), 4 * (T ? T : 1), 8 * (T ? T : 1), 8 * 256, 4 * 256,
                                   N, 6 * N, 8 * (T ? T : 1), 4 * (d.n_blocks ? d.n_blocks : 1)};
     for (int i = 0; i < BM25X_N_ARRAYS; i++) {
@@ -889,7 +900,8 @@ extern "C" int bm25x_index_alloc_replica(const bm25x_index_layout *like, int dev
     d.n_post_pad = like->n_postings_padded;
     d.n_blocks = like->n_blocks;
     const size_t T = d.n_terms, N = d.n_docs;
-    TRY(dev_alloc(ix, &d.post, d.n_post_pad + 2));
+    TRY(dev_alloc(ix, &d.post, d.n_post_pad + BM25X_POST_SLACK));
+    TRY(dev_alloc(ix, &d.pdoc, d.n_post_pad + BM25X_POST_SLACK));
     TRY(dev_alloc(ix, &d.post_off, T + 1));
     TRY(dev_alloc(ix, &d.df, T));
     TRY(dev_alloc(ix, &d.blk_off, T + 1));
@@ -912,6 +924,10 @@ extern "C" int bm25x_index_finalize_replica(bm25x_index *ix) {
         return BM25X_ERR_INVALID;
     }
     BM25X_CUDA_TRY(cudaSetDevice(ix->device));
+    // derived data that does not travel: the doc-id-only copy of the postings
+    k_extract_docs<<<148 * 8, 256>>>(ix->d.post, ix->d.n_post_pad + BM25X_POST_SLACK, ix->d.pdoc);
+    BM25X_CUDA_TRY(cudaGetLastError());
+    BM25X_CUDA_TRY(cudaDeviceSynchronize());
     ix->h_df.resize(ix->d.n_terms);
     if (ix->d.n_terms)
         BM25X_CUDA_TRY(cudaMemcpy(ix->h_df.data(), ix->d.df, sizeof(uint32_t) * ix->d.n_terms, cudaMemcpyDeviceToHost));

@@ -401,6 +401,7 @@ extern "C" int bm25x_batch_run(bm25x_batch *b, void *stream_v, bm25x_search_stat
         if (!g.nq) continue;
         SearchParams sp;
         sp.post = d.post;
+        sp.pdoc = d.pdoc;
         sp.post_off = d.post_off;
         sp.df = d.df;
         sp.blk_off = d.blk_off;

@@ -71,6 +71,27 @@ namespace {
 #ifndef BM25X_RING_ADAPT
 #define BM25X_RING_ADAPT 1  // 1: ring sizes per query ∝ df; 0: M equal rings
 #endif
+#ifndef BM25X_DOCRING
+#define BM25X_DOCRING 0  // 1: the 2..4-term classes stream DOC IDS ONLY (4 B per posting, SearchParams::pdoc): their hot loop
+                         // never reads tf / fieldnorm once no single-term posting can pass; the posting word is fetched
+                         // from HBM for the few postings that reach the verification.  Twice the postings per ring byte.
+#endif
+#ifndef BM25X_DOCRING_LOG_R
+#define BM25X_DOCRING_LOG_R 9  // doc ids per run of a DOCRING class (2 KiB per run, as 256 8-byte postings)
+#endif
+#ifndef BM25X_DOCRING_G
+#define BM25X_DOCRING_G 1  // 16-byte shared loads (4 doc ids) per lane and trip of a DOCRING class
+#endif
+#ifndef BM25X_DOCRING_TMAX
+#define BM25X_DOCRING_TMAX 3  // trips between two compactions of the detected postings of a DOCRING class
+#endif
+#ifndef BM25X_DOCRING_LOG_S
+#define BM25X_DOCRING_LOG_S 11  // log2 of the presence map bytes of a DOCRING class
+#endif
+#ifndef BM25X_RING_K2
+#define BM25X_RING_K2 1  // bit map only: TWO bits per document inside one 32-bit cell word (blocked Bloom filter, one
+                         // shared-memory atomicOr / one load as before): false alarms ~ (fill)^2 instead of fill
+#endif
 #ifndef BM25X_PRUNE_ALPHA
 #define BM25X_PRUNE_ALPHA 0.5  // terms leave the streamed set while the sum of their score bounds stays <= ALPHA · k-th score
 #endif
@@ -84,7 +105,11 @@ struct RCfg {
     static constexpr bool POOL_GLOBAL = KP_ > 2048;
     static constexpr size_t POOL_SMEM = POOL_GLOBAL ? 0 : (size_t)KP_;
     // ring postings per run: half a ring is in flight while the other half is processed
-    static constexpr int LOG_R = BM25X_RING_LOG_R > 0 ? BM25X_RING_LOG_R : (M_ <= 8 ? 8 : 7);
+    // doc-id-only rings (2..4 terms): ring element = u32 doc id, the posting word comes from HBM on demand
+    static constexpr bool DOCRING = (BM25X_DOCRING != 0) && M_ >= 2 && M_ <= 4;
+    using RT = typename std::conditional<DOCRING, uint32_t, Posting>::type;  // ring element
+    static constexpr uint32_t AL = DOCRING ? 4u : 2u;                        // ring elements per 16 bytes (TMA granularity)
+    static constexpr int LOG_R = DOCRING ? BM25X_DOCRING_LOG_R : (BM25X_RING_LOG_R > 0 ? BM25X_RING_LOG_R : (M_ <= 8 ? 8 : 7));
     static constexpr int R = 1 << LOG_R;   // ring postings per run when the M runs share the budget evenly
     // The warp's ring budget (M·R postings) is split per QUERY in proportion to the terms' df (power-of-two rings of
     // 2^LOG_RMIN .. 2^LOG_RMAX postings): head terms next to rare ones get wide windows instead of M equal rings of
@@ -95,13 +120,16 @@ struct RCfg {
     static constexpr bool ADAPT = (BM25X_RING_ADAPT != 0) && M_ >= 8;
     static constexpr int LOG_RMIN = 6;
     static constexpr int LOG_RMAX = (LOG_R + 2 > 10 ? 10 : LOG_R + 2) > LOG_R ? (LOG_R + 2 > 10 ? 10 : LOG_R + 2) : LOG_R;
-    static constexpr int LOG_S = M_ == 1 ? 8 : (BM25X_RING_LOG_S > 0 ? BM25X_RING_LOG_S : (BM25X_RING_BITMAP && M_ <= 4 ? 11 : 13));  // presence map bytes = dense accumulator bytes (unused for one term)
+    static constexpr int LOG_S = M_ == 1 ? 8 : DOCRING ? BM25X_DOCRING_LOG_S : (BM25X_RING_LOG_S > 0 ? BM25X_RING_LOG_S : (BM25X_RING_BITMAP && M_ <= 4 ? 11 : 13));  // presence map bytes = dense accumulator bytes (unused for one term)
     static constexpr uint32_t MAP_BYTES = M_ == 1 ? 256u : (BM25X_RING_MAPBYTES ? (uint32_t)BM25X_RING_MAPBYTES : (1u << LOG_S));
     static constexpr uint32_t ACC_DOCS = MAP_BYTES / 4u;
-    static constexpr int U = BM25X_RING_U;          // 16-byte shared loads (2 postings) per lane and trip
-    static constexpr int TRIP = 64 * U;             // postings per warp trip
-    static constexpr int TMAX = 32 / (2 * U) < 3 ? 32 / (2 * U) : 3;  // trips between two compactions of the detected postings
-                                                                      // (3: the list stays small enough for a 14th warp per SM)
+    static constexpr int U = DOCRING ? BM25X_DOCRING_G : BM25X_RING_U;  // 16-byte shared loads per lane and trip
+    static constexpr int E = DOCRING ? 4 : 2;       // postings per 16-byte load
+    static constexpr int PL = U * E;                // postings per lane and trip
+    static constexpr int TRIP = 32 * PL;            // postings per warp trip
+    // trips between two compactions of the detected postings (3: the list stays small enough for a 14th warp per SM)
+    static constexpr int TMAX = DOCRING ? BM25X_DOCRING_TMAX : (32 / PL < 3 ? 32 / PL : 3);
+    static_assert(PL * TMAX <= 32, "one detection bit per posting slot of a lane between two compactions");
     static constexpr int LCAP = TMAX * TRIP + 64;   // candidate list entries, 16 bits each (verified when > 64 are listed)
     static constexpr int INIT = BM25X_RING_INIT;    // postings per run in the very first load (a threshold exists early)
     // Single-buffered: the whole ring is one window; it is refilled AFTER the chunk (the load is exposed, but it comes
@@ -109,7 +137,7 @@ struct RCfg {
     // i.e. more resident warps.  Double-buffered (default): half a ring in flight while the other half is processed.
     static constexpr bool SB = BM25X_RING_SB != 0;
     static constexpr size_t off_ring = 0;
-    static constexpr size_t off_map = off_ring + (size_t)M_ * R * sizeof(Posting);
+    static constexpr size_t off_map = off_ring + (size_t)M_ * R * sizeof(RT);
     static constexpr size_t off_pool_s = off_map + (size_t)MAP_BYTES;
     static constexpr size_t off_pool_d = off_pool_s + POOL_SMEM * 8;
     static constexpr size_t off_pool_g = off_pool_d + POOL_SMEM * 4;
@@ -135,24 +163,32 @@ __device__ __forceinline__ uint32_t ring_slot(uint32_t doc, uint32_t bytes) { re
 // lower_bound of `doc` in ring positions [a, e) (posting indices of the term; the ring holds index i at i & RM).
 // Fixed LOG_R + 1 power-of-two steps, no data-dependent branch: every lane of a verification pass searches the same run,
 // and independent searches interleave (the while-loop form cost 135 warp instructions per search, profiles/r2b).
+__device__ __forceinline__ uint32_t ring_doc(const Posting *rg, uint32_t pos) { return rg[pos].doc; }
+__device__ __forceinline__ uint32_t ring_doc(const uint32_t *rg, uint32_t pos) { return rg[pos]; }
 template <class C, int TOP = C::LOG_RMAX>
-__device__ __forceinline__ uint32_t ring_lower_bound(const Posting *rg, uint32_t mask, uint32_t a, uint32_t e,
+__device__ __forceinline__ uint32_t ring_lower_bound(const typename C::RT *rg, uint32_t mask, uint32_t a, uint32_t e,
                                                      uint32_t doc) {
     uint32_t pos = a;  // every posting before pos is < doc
 #pragma unroll
     for (int s = TOP; s >= 0; --s) {
         const uint32_t probe = pos + (1u << s);
-        if (probe <= e && rg[(probe - 1u) & mask].doc < doc) pos = probe;
+        if (probe <= e && ring_doc(rg, (probe - 1u) & mask) < doc) pos = probe;
     }
     return pos;
 }
-// posting word of `doc` in [a, e), 0 when absent
+// posting word of `doc` in [a, e), 0 when absent.  gpost = the term's postings in HBM (posting index = ring index):
+// doc-id-only rings fetch the word from there.
 template <class C, int TOP = C::LOG_RMAX>
-__device__ __forceinline__ uint32_t ring_find(const Posting *rg, uint32_t mask, uint32_t a, uint32_t e, uint32_t doc) {
+__device__ __forceinline__ uint32_t ring_find(const typename C::RT *rg, uint32_t mask, uint32_t a, uint32_t e, uint32_t doc,
+                                              const Posting *gpost) {
     const uint32_t l = ring_lower_bound<C, TOP>(rg, mask, a, e, doc);
     if (l < e) {
-        const Posting v = rg[l & mask];
-        if (v.doc == doc) return v.w;
+        if constexpr (C::DOCRING) {
+            if (rg[l & mask] == doc) return __ldg(&gpost[l].w);
+        } else {
+            const Posting v = rg[l & mask];
+            if (v.doc == doc) return v.w;
+        }
     }
     return 0u;
 }
@@ -199,7 +235,8 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
     float *s1f = (float *)(smem + C::off_s1f);
     for (int i = threadIdx.x; i < 256; i += C::THREADS) s1f[i] = p.s1f[i];
     uint8_t *ws = smem + C::shared_bytes + C::warp_bytes * wid;
-    Posting *rings = (Posting *)(ws + C::off_ring);
+    using RT = typename C::RT;
+    RT *rings = (RT *)(ws + C::off_ring);
     uint8_t *map = ws + C::off_map;
     WPool<C> pl;
     if (C::POOL_GLOBAL) {
@@ -272,7 +309,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
         if (lane < (int)m) {
             const uint32_t term = p.q_terms[t0 + lane];
             dfj = p.df[term];
-            dfpad = (dfj + 1u) & ~1u;
+            dfpad = (dfj + C::AL - 1u) & ~(C::AL - 1u);  // whole 16-byte pieces (the lists are padded to 4 postings in HBM)
             pbase = p.post_off[term];
             bbase = p.blk_off[term];
             nbj = (dfj + BM25X_BLOCK - 1) / BM25X_BLOCK;
@@ -285,7 +322,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
         // the budget).
         uint32_t rlog = 0, rbase = 0, rsize = 2u, rmask = 1u;
         bool small_rings = true;  // every ring <= 2^LOG_R postings: searches need LOG_R + 1 steps only
-        Posting *myring = rings;
+        RT *myring = rings;
         auto alloc_rings = [&](uint32_t streamed) {
             if constexpr (!C::ADAPT) {  // M equal rings at fixed places
                 rlog = C::LOG_R;
@@ -369,6 +406,9 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
         float FloT = -1.f;         // filter threshold on the score over ALL terms (f.Flo: over the streamed terms only)
         bool thr_new = false;     // the threshold moved since the pruned set was last reconsidered
         uint32_t wlim = 255u;         // lane j: single-term postings of run j can pass only if w > wlim  (tf >= 1: all)
+#ifdef BM25X_DIAG_NOSOLO
+        wlim = 0xFFFFFFFFu;
+#endif
         uint32_t tiew = 0xFFFFFFFFu;  // lane j: posting word of the tie signature when it belongs to run j
 
         // f32 filter constants from (Sk, tie signature, pruned set)
@@ -393,6 +433,9 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
             // the term's best posting (its token-level bound) stays below the threshold: no posting of this run can
             // enter alone, the hot loop drops the single-term test altogether
             if (lane < (int)m && ubd < flo) wlim = 0xFFFFFFFFu;
+#ifdef BM25X_DIAG_NOSOLO  // timing diagnostics only (wrong results): no posting ever passes alone
+            wlim = 0xFFFFFFFFu;
+#endif
             tiew = (f.tie_dk != INF && (f.tie_sig >> 27) == (uint32_t)lane) ? (f.tie_sig & 0x07FFFFFFu) : 0xFFFFFFFFu;
         };
         // cut the pool back to k and refresh the threshold (Results::push / threshold, search.rs:284-314)
@@ -414,7 +457,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
             refresh_filter();
         }
 
-        // one refill round: lane j appends n postings (even) to its ring
+        // one refill round: lane j appends n postings (a multiple of AL = whole 16-byte pieces) to its ring
         auto issue_round = [&](uint32_t n) -> bool {
             const uint32_t total = __reduce_add_sync(FULL, n);
             if (total == 0u) return false;
@@ -422,15 +465,19 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
             // async-proxy writes
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
-            if (lane == 0) mbar_arrive_expect_tx(bar, total * (uint32_t)sizeof(Posting));
+            if (lane == 0) mbar_arrive_expect_tx(bar, total * (uint32_t)sizeof(RT));
             __syncwarp();
             if (n > 0) {
                 const uint32_t off = wr & rmask;
                 const uint32_t n1 = min(n, rsize - off);
-                const Posting *src = p.post + pbase + wr;
-                tma_load_1d(myring + off, src, n1 * (uint32_t)sizeof(Posting), bar);
-                if (n > n1) tma_load_1d(myring, src + n1, (n - n1) * (uint32_t)sizeof(Posting), bar);
-                fetched += min(wr + n, dfj) - min(wr, dfj);  // the pad slot of an odd list is not a posting
+                const RT *src;
+                if constexpr (C::DOCRING) src = p.pdoc + pbase + wr;
+                else src = p.post + pbase + wr;
+                tma_load_1d(myring + off, src, n1 * (uint32_t)sizeof(RT), bar);
+                if (n > n1) tma_load_1d(myring, src + n1, (n - n1) * (uint32_t)sizeof(RT), bar);
+#ifndef BM25X_DIAG_SOLOFRAC
+                fetched += min(wr + n, dfj) - min(wr, dfj);  // the pad slots of a list are not postings
+#endif
                 wr += n;
             }
             return true;
@@ -490,7 +537,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                         alloc_rings(~ne_mask);
                         uint32_t n = 0;
                         if (lane < (int)m && !((ne_mask >> lane) & 1u)) {
-                            wr = rd & ~1u;
+                            wr = rd & ~(C::AL - 1u);
                             n = min(rsize, dfpad - wr);
                         }
                         if (issue_round(n)) {
@@ -503,14 +550,14 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
             const bool act = lane < (int)m && !((ne_mask >> lane) & 1u);
             const uint32_t avail_e = min(wr, dfj);
             uint32_t limit = INF;  // runs with postings left in HBM bound the window by their last landed document
-            if (act && wr < dfj) limit = myring[(wr - 1u) & rmask].doc;
+            if (act && wr < dfj) limit = ring_doc(myring, (wr - 1u) & rmask);
             uint32_t hi = __reduce_min_sync(FULL, limit);
             bool last = hi == INF;
             uint32_t e = rd;
             {
                 // a window usually ends in the last few postings of every ring (all runs advance together): when the posting
                 // 32 before the end is still inside the window for every run, 6 search steps over that tail are enough
-                const bool tail = act && !last && avail_e - rd > 32u && myring[(avail_e - 33u) & rmask].doc < hi;
+                const bool tail = act && !last && avail_e - rd > 32u && ring_doc(myring, (avail_e - 33u) & rmask) < hi;
                 if (__all_sync(FULL, tail || !act || last)) {
                     if (act) e = last ? avail_e : ring_lower_bound<C, 5>(myring, rmask, avail_e - 32u, avail_e, hi);
                 } else if (act) {
@@ -528,7 +575,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                 chunk_postings = S;
                 const uint32_t S2 = __reduce_add_sync(FULL, n * n);
                 uint32_t hi_eff = hi;
-                if (last) hi_eff = __reduce_max_sync(FULL, n ? myring[(e - 1u) & rmask].doc + 1u : 0u);
+                if (last) hi_eff = __reduce_max_sync(FULL, n ? ring_doc(myring, (e - 1u) & rmask) + 1u : 0u);
                 span = hi_eff > lo ? hi_eff - lo : 0u;
                 dense = (unsigned long long)S * S - S2 > 2ull * BM25X_RING_DENSE_T * (unsigned long long)span;
                 if (dense && span > C::ACC_DOCS) {  // clamp the window to the accumulator: consume the rings partially
@@ -543,7 +590,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                 uint32_t n = 0;
                 if (act && wr < dfpad) {
                     const uint32_t fr = rsize - (wr - rd);
-                    n = min(min(fr, rsize / 2) & ~1u, dfpad - wr);
+                    n = min(min(fr, rsize / 2) & ~(C::AL - 1u), dfpad - wr);
                     // no small top-ups while the run still holds a quarter ring beyond this chunk
                     if (n < rsize / 8 && wr - e >= rsize / 4) n = 0;
                 }
@@ -567,7 +614,22 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                     own.doc = 0;
                     own.w = 0;
                     const uint32_t jbase = C::ADAPT ? __shfl_sync(FULL, rbase, j & 31u) : (j & 31u) * C::R;
-                    if (has && !by_doc) own = rings[jbase + (ent & 0x3FFu)];
+                    // doc-id-only rings: the listed posting's word stays in HBM until something needs it — a twin was
+                    // found, or run j can still pass alone (wlim): most false alarms of the map never touch HBM
+                    const Posting *gown = nullptr;  // DOCRING: &post[posting index] of the listed posting
+                    bool solo_j = false;
+                    if constexpr (C::DOCRING) {
+                        const uint32_t raj = __shfl_sync(FULL, rd, j & 31u);
+                        const uint64_t pbj = __shfl_sync(FULL, pbase, j & 31u);
+                        solo_j = __shfl_sync(FULL, wlim, j & 31u) != 0xFFFFFFFFu;
+                        if (has && !by_doc) {
+                            const uint32_t pos = ent & 0x3FFu;
+                            own.doc = rings[jbase + pos];
+                            gown = p.post + pbj + (raj + ((pos - raj) & ((uint32_t)C::R - 1u)));
+                        }
+                    } else {
+                        if (has && !by_doc) own = rings[jbase + (ent & 0x3FFu)];
+                    }
                     const uint32_t doc = by_doc ? lo + (ent & 0x7FFFu) : own.doc;
                     float F = 0.f;
                     uint32_t cnt = 0, sig = SIG_NONE;
@@ -577,9 +639,11 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
 #pragma unroll
                     for (int i = 0; i < (KEEPW ? C::M : 1); ++i) wv[i] = 0u;
                     auto holder = [&](int i, uint32_t ib, uint32_t im, uint32_t ai, uint32_t ei) -> uint32_t {
+                        const Posting *gi = nullptr;
+                        if constexpr (C::DOCRING) gi = p.post + __shfl_sync(FULL, pbase, i);  // (not reached: DOCRING has its own front end)
                         return (uint32_t)i == j ? own.w
-                                                : (small_rings ? ring_find<C, C::LOG_R>(rings + ib, im, ai, ei, doc)
-                                                               : ring_find<C>(rings + ib, im, ai, ei, doc));
+                                                : (small_rings ? ring_find<C, C::LOG_R>(rings + ib, im, ai, ei, doc, gi)
+                                                               : ring_find<C>(rings + ib, im, ai, ei, doc, gi));
                     };
                     auto filter_term = [&](int i) {
                         const uint32_t ai = __shfl_sync(FULL, rd, i), ei = __shfl_sync(FULL, e, i);
@@ -597,13 +661,55 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                         }
                         return wi;
                     };
-                    if (C::M == 3 && pairs) {
+                    if constexpr (C::DOCRING) {
+                        // searches first (doc ids in the rings), posting words of the holders from HBM afterwards
+                        bool found = false;
+                        if (C::M == 3 && pairs) {
+                            const uint32_t o = (lane & 1) ? (j == 2u ? 1u : 2u) : (j == 0u ? 1u : 0u);
+                            const uint32_t ao = __shfl_sync(FULL, rd, o), eo = __shfl_sync(FULL, e, o);
+                            const uint64_t pbo = __shfl_sync(FULL, pbase, o);
+                            uint32_t wo = 0u;
+                            if (has) wo = ring_find<C, C::LOG_R>(rings + o * C::R, C::R - 1u, ao, eo, doc, p.post + pbo);
+                            const uint32_t wx = __shfl_xor_sync(FULL, wo, 1);  // the partner's run
+                            const uint32_t ox = (lane & 1) ? (j == 0u ? 1u : 0u) : (j == 2u ? 1u : 2u);
+                            has = has && !(lane & 1);
+#pragma unroll
+                            for (int i = 0; i < C::M; ++i) wv[i] = (uint32_t)i == o ? wo : ((uint32_t)i == ox ? wx : 0u);
+                            found = (wo | wx) != 0u;
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < C::M; ++i) {
+                                const uint32_t ai = __shfl_sync(FULL, rd, i), ei = __shfl_sync(FULL, e, i);
+                                const uint64_t pbi = __shfl_sync(FULL, pbase, i);
+                                if (i < (int)m && has && (uint32_t)i != j && !((ne_mask >> i) & 1u)) {
+                                    wv[i] = ring_find<C, C::LOG_R>(rings + i * C::R, C::R - 1u, ai, ei, doc, p.post + pbi);
+                                    found = found || wv[i] != 0u;
+                                }
+                            }
+                        }
+                        if (!by_doc) {
+                            has = has && (found || solo_j);  // a lone posting of a run that cannot pass alone: dropped unread
+                            if (has) own.w = __ldg(&gown->w);
+                        }
+#pragma unroll
+                        for (int i = 0; i < C::M; ++i) {
+                            const float s0 = __shfl_sync(FULL, s0f, i);
+                            const uint32_t wi = (uint32_t)i == j ? own.w : wv[i];
+                            if (has && wi) {
+                                F += score_f32(wi, s0, s1f);
+                                cnt++;
+                                sig = make_sig(i, wi);
+                                later |= (uint32_t)i > j;
+                            }
+                            wv[i] = has ? wi : 0u;
+                        }
+                    } else if (C::M == 3 && pairs) {
                         if constexpr (C::M == 3) {
                             // my run to search: the first (even lane) or second (odd lane) of the two runs other than j
                             const uint32_t o = (lane & 1) ? (j == 2u ? 1u : 2u) : (j == 0u ? 1u : 0u);
                             const uint32_t ao = __shfl_sync(FULL, rd, o), eo = __shfl_sync(FULL, e, o);
                             uint32_t wo = 0u;
-                            if (has) wo = ring_find<C, C::LOG_R>(rings + o * C::R, C::R - 1u, ao, eo, doc);
+                            if (has) wo = ring_find<C, C::LOG_R>(rings + o * C::R, C::R - 1u, ao, eo, doc, nullptr);
                             const uint32_t wx = __shfl_xor_sync(FULL, wo, 1);  // the partner's run
                             const uint32_t ox = (lane & 1) ? (j == 0u ? 1u : 0u) : (j == 2u ? 1u : 2u);
                             has = has && !(lane & 1);
@@ -778,6 +884,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
             int rj = -1, variant = 0;
             bool multi = false;
             const uint4 *rg = nullptr;
+            const uint4 *gq = nullptr;  // DOCRING: the current run's 8-byte postings in HBM (single-term test only)
             int myvariant = 0;  // lane j: loop variant of run j in this window (4: single-term test, 2: test, 1: mark)
             if (!dense) {
                 todo = __ballot_sync(FULL, act && e > rd);
@@ -802,11 +909,16 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                     td &= td - 1u;
                     const uint32_t a = __shfl_sync(FULL, rd, j), ee = __shfl_sync(FULL, e, j);
                     const float s0 = __shfl_sync(FULL, s0f, j);
-                    const Posting *rgp = rings + ring_base(j);
+                    const RT *rgp = rings + ring_base(j);
                     const uint32_t jm = ring_mask(j);
-                    for (uint32_t i = a + lane; i < ee; i += 32) {
-                        const Posting v = rgp[i & jm];
-                        acc[v.doc - lo] += score_f32(v.w, s0, s1f);
+                    if constexpr (C::DOCRING) {  // the posting words of a dense window come straight from HBM
+                        const Posting *gp = p.post + __shfl_sync(FULL, pbase, j);
+                        for (uint32_t i = a + lane; i < ee; i += 32) acc[rgp[i & jm] - lo] += score_f32(__ldg(&gp[i].w), s0, s1f);
+                    } else {
+                        for (uint32_t i = a + lane; i < ee; i += 32) {
+                            const Posting v = rgp[i & jm];
+                            acc[v.doc - lo] += score_f32(v.w, s0, s1f);
+                        }
                     }
                     __syncwarp();
                 }
@@ -822,10 +934,20 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                 for (int t = 0; t < C::TMAX && pb < ree; ++t, pb += C::TRIP) {
                     uint4 q[C::U];
                     uint32_t ix[C::U];
+                    // DOCRING: tf / fieldnorm words only while a posting of this run can still pass alone (loop variants
+                    // with the single-term test): two 16-byte loads per four doc ids, straight from HBM / L2
+                    uint4 gw[C::DOCRING && SOLO ? C::U : 1][2];
 #pragma unroll
                     for (int u = 0; u < C::U; ++u) {
-                        ix[u] = pb + 2u * (uint32_t)(lane + 32 * u);
-                        q[u] = rg[(ix[u] >> 1) & (rm >> 1)];
+                        ix[u] = pb + (uint32_t)C::E * (uint32_t)(lane + 32 * u);
+                        q[u] = rg[(ix[u] / (uint32_t)C::E) & (rm / (uint32_t)C::E)];
+                        if constexpr (C::DOCRING && SOLO) {
+                            gw[u][0] = gw[u][1] = make_uint4(0u, 0u, 0u, 0u);
+                            if (ix[u] < ree) {  // ix is a multiple of 4 and the lists are padded to 4: in bounds
+                                gw[u][0] = __ldg(gq + (ix[u] >> 1));
+                                gw[u][1] = __ldg(gq + (ix[u] >> 1) + 1);
+                            }
+                        }
                     }
                     uint32_t bits = 0u;
                     auto body = [&](auto check_c) {
@@ -833,16 +955,30 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
 #pragma unroll
                         for (int u = 0; u < C::U; ++u) {
 #pragma unroll
-                            for (int h = 0; h < 2; ++h) {
-                                const uint32_t doc = h ? q[u].z : q[u].x, w = h ? q[u].w : q[u].y;
+                            for (int h = 0; h < C::E; ++h) {
+                                uint32_t doc, w = 0u;
+                                if constexpr (C::DOCRING) {
+                                    doc = h == 0 ? q[u].x : (h == 1 ? q[u].y : (h == 2 ? q[u].z : q[u].w));
+                                    if constexpr (SOLO) w = (h & 1) ? gw[u][h >> 1].w : gw[u][h >> 1].y;
+                                } else {
+                                    doc = h ? q[u].z : q[u].x;
+                                    w = h ? q[u].w : q[u].y;
+                                }
                                 const bool valid = !CHECK || ix[u] + h - ra < rnj;  // unsigned: also false below ra
                                 bool c = false;
                                 if (TEST || MARK) {
 #if BM25X_RING_BITMAP
-                                    const uint32_t slot = ring_slot(doc, C::MAP_BYTES * 8u);
+                                    const uint32_t hsh = doc * 0x9E3779B1u;
+                                    const uint32_t slot = __umulhi(hsh, C::MAP_BYTES * 8u);
                                     uint32_t *cell = (uint32_t *)map + (slot >> 5);
+#if BM25X_RING_K2
+                                    const uint32_t msk = (1u << (slot & 31u)) | (1u << ((hsh >> 7) & 31u));
+                                    if (TEST) c = (*cell & msk) == msk;
+                                    if (MARK && valid) atomicOr(cell, msk);
+#else
                                     if (TEST) c = (*cell >> (slot & 31u)) & 1u;
                                     if (MARK && valid) atomicOr(cell, 1u << (slot & 31u));
+#endif
 #else
                                     const uint32_t slot = ring_slot(doc, C::MAP_BYTES);
                                     if (TEST) c = map[slot] == genv;
@@ -850,13 +986,13 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
 #endif
                                 }
                                 if (SOLO) c = c | ((w > wl) & !((w == tw) & (doc > tdk)));  // bitwise: no branches
-                                bits |= (uint32_t)(valid & c) << (2 * u + h);
+                                bits |= (uint32_t)(valid & c) << (C::E * u + h);
                             }
                         }
                     };
                     if (pb >= ra && pb + C::TRIP <= ree) body(std::false_type());
                     else body(std::true_type());
-                    hm |= bits << (2 * C::U * t);
+                    hm |= bits << (C::PL * t);
                 }
                 for (;;) {  // compaction: one listed posting per lane and round
                     const uint32_t bal = __ballot_sync(FULL, hm != 0u);
@@ -864,8 +1000,8 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                     if (hm) {
                         const uint32_t bpos = (uint32_t)__ffs(hm) - 1u;
                         hm &= hm - 1u;
-                        const uint32_t t = bpos / (2 * C::U), sl = bpos % (2 * C::U);
-                        const uint32_t idx = pb0 + t * C::TRIP + 2u * (uint32_t)(lane + 32 * (sl >> 1)) + (sl & 1u);
+                        const uint32_t t = bpos / C::PL, sl = bpos % C::PL;
+                        const uint32_t idx = pb0 + t * C::TRIP + (uint32_t)C::E * (uint32_t)(lane + 32 * (sl / C::E)) + (sl % C::E);
                         cand[nc + __popc(bal & lt_mask)] = (uint16_t)(((uint32_t)rj << 10) | (idx & rm));
                     }
                     nc += __popc(bal);
@@ -892,9 +1028,10 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                             variant = __shfl_sync(FULL, myvariant, rj);
                             rnj = ree - ra;
                             rg = (const uint4 *)(rings + ring_base(rj));
+                            if constexpr (C::DOCRING) gq = (const uint4 *)(p.post + __shfl_sync(FULL, pbase, rj));
                             rm = ring_mask(rj);
                             tdk = f.tie_dk;  // snapshot with tw: a stale (looser) pair stays valid, thresholds only tighten
-                            pb = ra & ~1u;
+                            pb = ra & ~((uint32_t)C::E - 1u);
                         }
                         switch (variant) {
                             case 0: pb = ree; break;  // nothing to learn from this run in this window
@@ -925,6 +1062,9 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                 }
                 if (nc) verify();
             }
+#ifdef BM25X_DIAG_SOLOFRAC  // statistics diagnostics: `fetched` counts the postings consumed while some run can pass alone
+            if (__any_sync(FULL, act && wlim != 0xFFFFFFFFu)) fetched += e - rd;
+#endif
             rd = e;
             }  // sub-windows
             lo = hi;
@@ -932,13 +1072,20 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
             if (C::SB) {  // single-buffered: refill everything this chunk freed; the bytes should already sit in L2
                 uint32_t n = 0;
                 if (act && wr < dfpad) {
-                    n = min((rsize - (wr - rd)) & ~1u, dfpad - wr);
+                    n = min((rsize - (wr - rd)) & ~(C::AL - 1u), dfpad - wr);
                     if (n < rsize / 4 && wr - rd >= rsize / 4) n = 0;  // no small top-ups
                 }
                 inflight = issue_round(n);
                 if (n > 0 && wr < dfpad) {  // the round after this one: into L2 while this chunk's successor is processed
-                    const uint32_t pf = min(rsize, dfpad - wr) * (uint32_t)sizeof(Posting);
-                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.post + pbase + wr), "r"(pf) : "memory");
+                    const uint32_t pn_ = min(rsize, dfpad - wr);
+                    if constexpr (C::DOCRING) {
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.pdoc + pbase + wr), "r"(pn_ * 4u) : "memory");
+                        // while postings of this run can still pass alone, the loop also reads their tf / fieldnorm words
+                        if (wlim != 0xFFFFFFFFu)
+                            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.post + pbase + wr), "r"(pn_ * 8u) : "memory");
+                    } else {
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.post + pbase + wr), "r"(pn_ * 8u) : "memory");
+                    }
                 }
             }
         }
