@@ -134,7 +134,9 @@ int bm25x_index_finalize_replica(bm25x_index *idx);
 /* Options.  "prune" (default 1): MaxScore-style pruning in the warp-per-query kernel — terms whose summed score upper
  * bounds (the token-level WAND bound of the reference: TokenTuple.wand_fieldnorm/wand_term_frequency,
  * flush.rs:101-120, search.rs:363) stay below 5 % of the current k-th score are no longer streamed; their postings
- * are looked up in HBM only for the candidates.  Results are identical with it on or off. */
+ * are looked up in HBM only for the candidates.  Results are identical with it on or off.
+ * "twophase" (default 1): queries of 2..4 terms with limit <= 224 run as two launches — 8-byte postings while single
+ * postings can still enter the top-k, then doc ids only (half the bytes) for the rest.  Results identical on or off. */
 int bm25x_index_set_option(bm25x_index *idx, const char *name, int64_t value);
 /* df of every term (TokenTuple.number_of_documents), host copy. */
 int bm25x_index_get_df(const bm25x_index *idx, uint32_t *df_out);

@@ -16,6 +16,10 @@
                                     // the doc-id-only copy (pdoc, 4 B per posting) as well as of the 8-byte postings
 #define BM25X_POST_SLACK 4u         // slack slots behind the last list, reading as exhausted cursors
 
+#ifndef BM25X_TWOPHASE_DEFAULT
+#define BM25X_TWOPHASE_DEFAULT 1
+#endif
+
 void bm25x_set_error(const char *fmt, ...);
 // Host threads this process may really use: the affinity mask capped by the cgroup CPU quota (omp_get_max_threads()
 // ignores the quota: 128 threads spinning on a dozen granted cores cost the batch canonicalisation tens of ms).
@@ -75,6 +79,7 @@ struct bm25x_index {
     cudaStream_t stream = nullptr;
     std::vector<void *> allocs;
     int prune = 1;                     // MaxScore-style pruning in the search kernels
+    int twophase = BM25X_TWOPHASE_DEFAULT;  // 2..4-term classes, k <= 224: two launches (8-byte postings, then doc ids only)
     // page-locked staging buffer of bm25x_batch_prepare (grow-only, shared by the batches of this index)
     uint32_t *h_stage = nullptr;
     size_t h_stage_words = 0;

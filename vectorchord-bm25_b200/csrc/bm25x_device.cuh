@@ -4,6 +4,17 @@
 
 #include "bm25x_common.h"
 
+// Two-phase launches of the 2..4-term classes (bm25x_search_ring.cuh, RCfg::PH): what the first phase hands over when it
+// suspends a query — the pool entries themselves travel in the query's output rows.
+struct ResumeRec {
+    double Sk, ub_ne;
+    unsigned long long fetched_unused;
+    uint32_t rd[4];           // postings consumed per run
+    float ne_prefix[4];       // lane t: Σ bounds of the terms pruned before the t-th one
+    uint32_t lo, pn, dk, tie_sig, ne_mask, n_ne, ne_list, pad_;
+};
+static_assert(sizeof(ResumeRec) == 88, "ResumeRec layout");
+
 // One launch = the queries of one term-count class (shared by the translation units of the library).
 struct SearchParams {
     const Posting *post;
@@ -19,6 +30,10 @@ struct SearchParams {
     const float *s1f;
     const uint16_t *payload;
     const double *ubd;                  // per-term upper bound of one posting's exact score
+    // two-phase launches: q2[0] = number of suspended queries, q2[1] = the second phase's work counter, q2[2..] = their
+    // positions in this launch's query list; resume[position] = the hand-over record
+    uint32_t *q2;
+    ResumeRec *resume;
     unsigned long long *fetched;        // Σ postings actually loaded into shared memory (pruning statistics)
     uint8_t *pool_scratch;              // k > 1024: per-warp candidate pools in HBM (k_search_ring, RCfg::POOL_GLOBAL)
     int prune;

@@ -955,6 +955,10 @@ extern "C" int bm25x_index_set_option(bm25x_index *ix, const char *name, int64_t
         ix->prune = value != 0;
         return BM25X_OK;
     }
+    if (strcmp(name, "twophase") == 0) {  // 2..4-term classes: 8-byte postings first, doc ids only once no posting passes alone
+        ix->twophase = value != 0;
+        return BM25X_OK;
+    }
     bm25x_set_error("bm25x_index_set_option: unknown option '%s'", name);
     return BM25X_ERR_INVALID;
 }

@@ -77,6 +77,9 @@ struct Group {
     uint32_t nq = 0;
     uint32_t *d_ids = nullptr, *d_off = nullptr, *d_terms = nullptr;  // slices of one device buffer
     int *d_counter = nullptr;
+    // two-phase launches (2..4 terms, k <= 224): suspended-query list + hand-over records (bm25x_device.cuh)
+    uint32_t *d_q2 = nullptr;
+    ResumeRec *d_resume = nullptr;
 };
 
 struct bm25x_batch {
@@ -98,16 +101,20 @@ struct bm25x_batch {
 };
 
 // kernel v6 (bm25x_search_ring.cu: warp per query, ring stages + presence map), one entry per pool capacity
-int bm25x_launch_ring_kp64(int device, int sm_count, const SearchParams &sp, int M, cudaStream_t stream);
-int bm25x_launch_ring_kp256(int device, int sm_count, const SearchParams &sp, int M, cudaStream_t stream);
-int bm25x_launch_ring_kp2048(int device, int sm_count, const SearchParams &sp, int M, cudaStream_t stream);
-int bm25x_launch_ring_kp131072(int device, int sm_count, const SearchParams &sp, int M, cudaStream_t stream);
+// phase: 0 = the launch answers its queries; 1 / 2 = the two launches of a two-phase class (RCfg::PH)
+int bm25x_launch_ring_kp64(int device, int sm_count, const SearchParams &sp, int M, int phase, cudaStream_t stream);
+int bm25x_launch_ring_kp256(int device, int sm_count, const SearchParams &sp, int M, int phase, cudaStream_t stream);
+int bm25x_launch_ring_kp2048(int device, int sm_count, const SearchParams &sp, int M, int phase, cudaStream_t stream);
+int bm25x_launch_ring_kp131072(int device, int sm_count, const SearchParams &sp, int M, int phase, cudaStream_t stream);
 
-static int launch_ring_k(const bm25x_index *ix, const SearchParams &sp, int M, cudaStream_t stream) {
-    if (sp.k <= 32) return bm25x_launch_ring_kp64(ix->device, ix->sm_count, sp, M, stream);
-    if (sp.k <= 224) return bm25x_launch_ring_kp256(ix->device, ix->sm_count, sp, M, stream);
-    if (sp.k <= 1024) return bm25x_launch_ring_kp2048(ix->device, ix->sm_count, sp, M, stream);
-    return bm25x_launch_ring_kp131072(ix->device, ix->sm_count, sp, M, stream);  // candidate pools in HBM
+// Two launches per class: 2..4 terms with the pool in shared memory (k <= 224).
+static bool two_phase_class(const bm25x_index *ix, int M, uint32_t k) { return ix->twophase && M >= 2 && M <= 4 && k <= 224; }
+
+static int launch_ring_k(const bm25x_index *ix, const SearchParams &sp, int M, int phase, cudaStream_t stream) {
+    if (sp.k <= 32) return bm25x_launch_ring_kp64(ix->device, ix->sm_count, sp, M, phase, stream);
+    if (sp.k <= 224) return bm25x_launch_ring_kp256(ix->device, ix->sm_count, sp, M, phase, stream);
+    if (sp.k <= 1024) return bm25x_launch_ring_kp2048(ix->device, ix->sm_count, sp, M, 0, stream);
+    return bm25x_launch_ring_kp131072(ix->device, ix->sm_count, sp, M, 0, stream);  // candidate pools in HBM
 }
 
 template <typename T>
@@ -353,6 +360,13 @@ extern "C" int bm25x_batch_prepare(bm25x_index *ix, uint32_t nq, const uint32_t 
         BTRY(batch_alloc(b, &b->d_allow, nb));
         e = cudaMemcpyAsync(b->d_allow, allow, nb, cudaMemcpyHostToDevice, st);
     }
+    for (int c = 0; c < kNumClasses; ++c) {
+        Group &g = b->groups[c];
+        if (g.nq && two_phase_class(ix, g.M, k)) {
+            BTRY(batch_alloc(b, &g.d_q2, (size_t)g.nq + 2));
+            BTRY(batch_alloc(b, &g.d_resume, (size_t)g.nq));
+        }
+    }
     size_t slots = (size_t)nq * k;
     if (slots == 0) slots = 1;
     BTRY(batch_alloc(b, &b->d_out_doc, slots));
@@ -430,8 +444,20 @@ extern "C" int bm25x_batch_run(bm25x_batch *b, void *stream_v, bm25x_search_stat
         sp.out_payload = b->d_out_payload;
         sp.out_n = b->d_out_n;
         BM25X_CUDA_TRY(cudaMemsetAsync(g.d_counter, 0, sizeof(int), st));
+        sp.q2 = g.d_q2;
+        sp.resume = g.d_resume;
         int rc = BM25X_OK;
-        rc = launch_ring_k(ix, sp, g.M, st);
+        if (g.d_q2 && ix->twophase) {
+            // first phase: 8-byte postings until no posting can enter the top-k alone; second phase: the suspended
+            // queries go on with doc ids only (bm25x_search_ring.cuh, RCfg::PH)
+            BM25X_CUDA_TRY(cudaMemsetAsync(g.d_q2, 0, 2 * sizeof(uint32_t), st));
+            rc = launch_ring_k(ix, sp, g.M, 1, st);
+            if (rc != BM25X_OK) return rc;
+            launches++;
+            rc = launch_ring_k(ix, sp, g.M, 2, st);
+        } else {
+            rc = launch_ring_k(ix, sp, g.M, 0, st);
+        }
         if (rc != BM25X_OK) return rc;
         launches++;
     }

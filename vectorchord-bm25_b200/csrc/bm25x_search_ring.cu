@@ -39,8 +39,26 @@ int launch_ring(int device, int sm_count, const SearchParams &sp_in, cudaStream_
 #define BM25X_RING_ENTRY2(kp) bm25x_launch_ring_kp##kp
 #define BM25X_RING_ENTRY(kp) BM25X_RING_ENTRY2(kp)
 
-// M = term-count class of the launch (1, 2, 3, 4, 8, 16, 32)
-int BM25X_RING_ENTRY(BM25X_RING_KP)(int device, int sm_count, const SearchParams &sp, int M, cudaStream_t stream) {
+// M = term-count class of the launch (1, 2, 3, 4, 8, 16, 32); phase = RCfg::PH (1 / 2 only for 2..4 terms, KP <= 256)
+int BM25X_RING_ENTRY(BM25X_RING_KP)(int device, int sm_count, const SearchParams &sp, int M, int phase, cudaStream_t stream) {
+#if BM25X_RING_KP <= 256
+    if (phase == 1) switch (M) {
+            case 2: return launch_ring<RCfg<2, BM25X_RING_KP, 1>>(device, sm_count, sp, stream);
+            case 3: return launch_ring<RCfg<3, BM25X_RING_KP, 1>>(device, sm_count, sp, stream);
+            case 4: return launch_ring<RCfg<4, BM25X_RING_KP, 1>>(device, sm_count, sp, stream);
+            default: break;
+        }
+    if (phase == 2) switch (M) {
+            case 2: return launch_ring<RCfg<2, BM25X_RING_KP, 2>>(device, sm_count, sp, stream);
+            case 3: return launch_ring<RCfg<3, BM25X_RING_KP, 2>>(device, sm_count, sp, stream);
+            case 4: return launch_ring<RCfg<4, BM25X_RING_KP, 2>>(device, sm_count, sp, stream);
+            default: break;
+        }
+#endif
+    if (phase != 0) {
+        bm25x_set_error("k_search_ring: no two-phase launch for %d terms / pool %d", M, (int)BM25X_RING_KP);
+        return BM25X_ERR_INVALID;
+    }
     switch (M) {
         case 1: return launch_ring<RCfg<1, BM25X_RING_KP>>(device, sm_count, sp, stream);
         case 2: return launch_ring<RCfg<2, BM25X_RING_KP>>(device, sm_count, sp, stream);

@@ -92,13 +92,22 @@ namespace {
 #define BM25X_RING_K2 1  // bit map only: TWO bits per document inside one 32-bit cell word (blocked Bloom filter, one
                          // shared-memory atomicOr / one load as before): false alarms ~ (fill)^2 instead of fill
 #endif
+#ifndef BM25X_SUSPEND_MIN
+#define BM25X_SUSPEND_MIN 4096  // first phase: a query is handed to the doc-id-only phase when at least this many postings remain
+#endif
 #ifndef BM25X_PRUNE_ALPHA
 #define BM25X_PRUNE_ALPHA 0.5  // terms leave the streamed set while the sum of their score bounds stays <= ALPHA · k-th score
 #endif
 
-template <int M_, int KP_>
+// PH_: 0 = one launch answers the query.  Two-phase launches of the 2..4-term classes: 1 = first phase (8-byte postings in
+// the rings: every posting's tf / fieldnorm word is at hand while single-term postings can still enter the top-k), which
+// SUSPENDS a query as soon as no posting can pass alone any more; 2 = second phase (doc-id-only rings: twice the postings
+// per ring byte, half the bytes from HBM), which resumes the suspended queries.
+template <int M_, int KP_, int PH_ = 0>
 struct RCfg {
     static constexpr int M = M_;    // max live terms (lanes 0..M-1 own the terms)
+    static constexpr int PH = PH_;
+    static_assert(PH_ == 0 || (M_ >= 2 && M_ <= 4 && KP_ <= 256), "two-phase launches: 2..4 terms, pools in shared memory");
     static constexpr int KP = KP_;  // pool capacity (power of two >= k + 32)
     // pools beyond 2048 entries (k > 1024, up to the reference's bm25.limit maximum of 65535, src/index/gucs.rs:37-46)
     // live in HBM: one KP-entry slice of SearchParams::pool_scratch per warp
@@ -106,7 +115,7 @@ struct RCfg {
     static constexpr size_t POOL_SMEM = POOL_GLOBAL ? 0 : (size_t)KP_;
     // ring postings per run: half a ring is in flight while the other half is processed
     // doc-id-only rings (2..4 terms): ring element = u32 doc id, the posting word comes from HBM on demand
-    static constexpr bool DOCRING = (BM25X_DOCRING != 0) && M_ >= 2 && M_ <= 4;
+    static constexpr bool DOCRING = PH_ == 2 || (PH_ == 0 && (BM25X_DOCRING != 0) && M_ >= 2 && M_ <= 4);
     using RT = typename std::conditional<DOCRING, uint32_t, Posting>::type;  // ring element
     static constexpr uint32_t AL = DOCRING ? 4u : 2u;                        // ring elements per 16 bytes (TMA granularity)
     static constexpr int LOG_R = DOCRING ? BM25X_DOCRING_LOG_R : (BM25X_RING_LOG_R > 0 ? BM25X_RING_LOG_R : (M_ <= 8 ? 8 : 7));
@@ -266,9 +275,18 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
 
     for (;;) {
         int qi = 0;
-        if (lane == 0) qi = atomicAdd(p.work_counter, 1);
-        qi = __shfl_sync(FULL, qi, 0);
-        if (qi >= (int)p.nq) break;
+        if constexpr (C::PH == 2) {  // the suspended queries of the first phase, in the order they were handed over
+            if (lane == 0) {
+                const uint32_t i = atomicAdd(&p.q2[1], 1u);
+                qi = i < p.q2[0] ? (int)p.q2[2u + i] : -1;
+            }
+            qi = __shfl_sync(FULL, qi, 0);
+            if (qi < 0) break;
+        } else {
+            if (lane == 0) qi = atomicAdd(p.work_counter, 1);
+            qi = __shfl_sync(FULL, qi, 0);
+            if (qi >= (int)p.nq) break;
+        }
         const uint32_t qid = p.q_ids[qi];
         const uint32_t t0q = p.q_off[qi];
         const uint32_t m_total = p.q_off[qi + 1] - t0q;
@@ -289,6 +307,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
         f.tie_sig = SIG_NONE;
         f.tie_dk = INF;
         f.ctf = 0.f;
+        bool suspended = false;  // first phase: the query goes on in the second phase
         for (int pass = 0; pass < (mp ? 2 : 1); ++pass) {
         const uint32_t t0 = t0q + (pass ? 32u : 0u);
         const uint32_t m = mp ? (pass ? m_total - 32u : 32u) : m_total;
@@ -483,7 +502,36 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
             return true;
         };
 
-        bool inflight = issue_round(lane < (int)m ? min(dfpad, (uint32_t)C::INIT) : 0u);
+        bool inflight;
+        if constexpr (C::PH == 2) {
+            // ---- resume: cursors, threshold, pruned set from the record; the pool entries from the query's output rows ----
+            const ResumeRec *rec = p.resume + qi;
+            const size_t ob = (size_t)qid * k;
+            pn = (int)rec->pn;
+            for (int i = lane; i < pn; i += 32) {
+                pl.s[i] = (uint64_t)__double_as_longlong(p.out_score64[ob + i]);
+                pl.d[i] = p.out_doc[ob + i];
+                pl.g[i] = __float_as_uint(p.out_score[ob + i]);
+            }
+            if (lane < (int)m) rd = rec->rd[lane];
+            if (lane < 4) ne_prefix_f = rec->ne_prefix[lane];
+            lo = rec->lo;
+            f.tv = true;
+            f.Sk = rec->Sk;
+            f.dk = rec->dk;
+            f.tie_sig = rec->tie_sig;
+            ne_mask = rec->ne_mask;
+            n_ne = (int)rec->n_ne;
+            ne_list = rec->ne_list;
+            ub_ne = rec->ub_ne;
+            thr_new = true;
+            refresh_filter();
+            __syncwarp();
+            wr = rd & ~(C::AL - 1u);
+            inflight = issue_round(lane < (int)m && !((ne_mask >> lane) & 1u) ? min(rsize, dfpad - wr) : 0u);
+        } else {
+            inflight = issue_round(lane < (int)m ? min(dfpad, (uint32_t)C::INIT) : 0u);
+        }
 #ifdef BM25X_WATCHDOG
         uint32_t wd_chunks = 0;
 #endif
@@ -548,6 +596,41 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                 }
             }
             const bool act = lane < (int)m && !((ne_mask >> lane) & 1u);
+            if constexpr (C::PH == 1) {
+                // ---- hand-over: no posting of a streamed run can enter the top-k alone any more (wlim), so the rest of the
+                // query only needs doc ids — suspend it for the second phase.  Nothing is in flight here (the round has
+                // landed); the pool travels in the query's own output rows, the rest in the record.
+                if (!mp && f.tv && __all_sync(FULL, !act || wlim == 0xFFFFFFFFu) &&
+                    __reduce_add_sync(FULL, act ? dfj - rd : 0u) >= (uint32_t)BM25X_SUSPEND_MIN) {
+                    if (pn > (int)k) pool_cut();
+                    const size_t ob = (size_t)qid * k;
+                    for (int i = lane; i < pn; i += 32) {
+                        p.out_score64[ob + i] = __longlong_as_double((long long)pl.s[i]);
+                        p.out_doc[ob + i] = pl.d[i];
+                        p.out_score[ob + i] = __uint_as_float(pl.g[i]);
+                    }
+                    ResumeRec *rec = p.resume + qi;
+                    if (lane < 4) {
+                        rec->rd[lane] = rd;
+                        rec->ne_prefix[lane] = ne_prefix_f;
+                    }
+                    if (lane == 0) {
+                        rec->Sk = f.Sk;
+                        rec->ub_ne = ub_ne;
+                        rec->lo = lo;
+                        rec->pn = (uint32_t)pn;
+                        rec->dk = f.dk;
+                        rec->tie_sig = f.tie_sig;
+                        rec->ne_mask = ne_mask;
+                        rec->n_ne = (uint32_t)n_ne;
+                        rec->ne_list = ne_list;
+                        const uint32_t at = atomicAdd(&p.q2[0], 1u);
+                        p.q2[2u + at] = (uint32_t)qi;
+                    }
+                    suspended = true;
+                    break;
+                }
+            }
             const uint32_t avail_e = min(wr, dfj);
             uint32_t limit = INF;  // runs with postings left in HBM bound the window by their last landed document
             if (act && wr < dfj) limit = ring_doc(myring, (wr - 1u) & rmask);
@@ -1090,8 +1173,18 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
             }
         }
         // ---- Results::into_sorted_vec (search.rs:281) (after the last pass; between passes: a tidy pool and threshold) ----
-        if (pn > 0) pool_cut();
+        if (pn > 0 && !suspended) pool_cut();
         }  // passes
+        if (suspended) {  // no result rows yet; the statistics of this phase are final
+            if (p.fetched) {
+                fetched += probe_steps;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) fetched += __shfl_xor_sync(FULL, fetched, o);
+                if (lane == 0) atomicAdd(p.fetched, fetched);
+            }
+            __syncwarp();
+            continue;
+        }
         const size_t obase = (size_t)qid * k;
         for (uint32_t i = lane; i < k; i += 32) {
             uint32_t d = INF;
