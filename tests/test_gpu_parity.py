@@ -131,6 +131,30 @@ def test_pruning_on_off_identical(m, orc):
     ix.close()
 
 
+@pytest.mark.parametrize("zipf", [0.0, 1.0], ids=["uniform", "zipf"])
+def test_kernel_paths_identical(m, orc, zipf):
+    """The three ways a 2..4-term query can run — seeded launch (champion lists + doc-id-only stream), two-phase launches
+    (8-byte postings, then doc ids only), one unseeded launch — return the same bits, with pruning on and off, for limits
+    around the champion-list length (128) and the two-phase limit (224); a sample is checked against the oracle."""
+    c = m.synth_corpus(81, 80000, 400 if zipf == 0.0 else 4000, 6, 40, zipf)
+    q_off, q_terms = m.synth_queries(82, 160, c.n_terms, 2, 4, c.post_off, zipf)
+    ix = m.Index.from_corpus(c)
+    oix = _oracle_index(orc, c)
+    for k in (1, 10, 100, 128, 129, 224):
+        for prune in (1, 0):
+            ix.set_option("prune", prune)
+            got = {}
+            for name, (seed, two) in dict(seeded=(1, 0), twophase=(0, 1), plain=(0, 0)).items():
+                ix.set_option("seed", seed)
+                ix.set_option("twophase", two)
+                got[name] = ix.search_batch(q_off, q_terms, k)
+            for name in ("seeded", "twophase"):
+                for key in ("doc", "score", "score64", "n"):
+                    assert np.array_equal(got[name][key], got["plain"][key]), (name, key, k, prune)
+        _compare(got["seeded"], oix, q_off[:25], q_terms, k, what=f"paths k={k}")
+    ix.close()
+
+
 def test_evaluate_matches_oracle_bitwise(m, orc):
     c = m.synth_corpus(51, 5000, 400, 2, 120, 0.8)
     ix = m.Index.from_corpus(c)

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Times library variants / kernel generations side by side on ONE GPU and checks that all return the same bits.
 
-  python tools/time_variants.py NAME ...      NAME = variants/libbm25x_NAME.so ("main" = the in-tree library)
+  python tools/time_variants.py NAME[@opt=v,...] ...   NAME = variants/libbm25x_NAME.so ("main" = the in-tree library),
+                                                       opt=v = bm25x_index_set_option of that run (e.g. main@seed=0,twophase=1)
 Env: VAR_DOCS (default 10M), VAR_WORKLOADS (comma list of c3,c3k100,c5mix,c2,c4).  Every variant runs in its own process.
 """
 import hashlib
@@ -30,6 +31,9 @@ def one(docs, workloads):
     zipf_corpus = os.environ.get("VAR_CORPUS", "uniform") == "zipf"
     c = m.synth_corpus(0xB25C0DE0 + (4 if zipf_corpus else 3), docs, 100_000, 128, 128, 1.0 if zipf_corpus else 0.0)
     ix = m.Index.from_corpus(c)
+    for kv in filter(None, os.environ.get("VAR_OPTS", "").split(",")):  # NAME@opt=v,opt=v: index options of this variant
+        name, _, v = kv.partition("=")
+        ix.set_option(name, int(v))
     out = {"build_s": round(time.time() - t0, 1)}
     for name in workloads:
         nq, tmin, tmax, k, zipf = WL[name]
@@ -61,6 +65,7 @@ def main():
     for spec in sys.argv[1:]:
         name, _, gen = spec.partition("@")
         env = dict(os.environ)
+        env["VAR_OPTS"] = gen
         if name != "main":
             env["BM25X_LIBRARY"] = os.path.join(ROOT, "vectorchord-bm25_b200", "variants", f"libbm25x_{name}.so")
         try:

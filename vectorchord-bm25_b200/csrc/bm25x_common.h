@@ -14,10 +14,11 @@
 #define BM25X_DOC_INF 0xFFFFFFFFu   // exhausted-cursor sentinel, as search.rs:484-496
 #define BM25X_POST_ALIGN 4u         // every term's posting list starts on a multiple of 4 postings: 16-byte TMA granularity of
                                     // the doc-id-only copy (pdoc, 4 B per posting) as well as of the 8-byte postings
+#define BM25X_CHAMP_L 128u          // champion list: the best min(df, 128) postings of every term by single-term score
 #define BM25X_POST_SLACK 4u         // slack slots behind the last list, reading as exhausted cursors
 
 #ifndef BM25X_TWOPHASE_DEFAULT
-#define BM25X_TWOPHASE_DEFAULT 1
+#define BM25X_TWOPHASE_DEFAULT 0
 #endif
 
 void bm25x_set_error(const char *fmt, ...);
@@ -52,6 +53,13 @@ struct DeviceIndex {
     Posting *post = nullptr;        // [n_post_pad] term-major, doc-ascending inside a term
     uint32_t *pdoc = nullptr;       // [n_post_pad] the doc ids of `post` alone (derived on the device, not replicated): what the
                                     // 2..4-term classes of k_search_ring stream — their hot loop never reads tf / fieldnorm
+    // Champion lists (derived on the device, not replicated): per term its best min(df, BM25X_CHAMP_L) postings in the
+    // result order (exact single-term score desc, doc id asc).  A document that holds ONE query term can only be in the
+    // top-k if it is among the first k champions of that term (every posting ranked before it belongs to a document that
+    // beats it), so a query seeds its pool from these and its stream never tests single postings (RCfg::SEEDED).
+    Posting *champ = nullptr;       // [champ_off[n_terms]]
+    uint64_t *champ_off = nullptr;  // [n_terms+1]
+    uint64_t n_champ = 0;
     uint64_t *post_off = nullptr;   // [n_terms+1] padded offsets (multiples of BM25X_POST_ALIGN)
     uint32_t *df = nullptr;         // [n_terms] TokenTuple.number_of_documents
     uint64_t *blk_off = nullptr;    // [n_terms+1] first block index of each term
@@ -79,6 +87,7 @@ struct bm25x_index {
     cudaStream_t stream = nullptr;
     std::vector<void *> allocs;
     int prune = 1;                     // MaxScore-style pruning in the search kernels
+    int seed = 1;                      // 2..4-term classes, k <= BM25X_CHAMP_L, no prefilter: pools seeded from the champion lists
     int twophase = BM25X_TWOPHASE_DEFAULT;  // 2..4-term classes, k <= 224: two launches (8-byte postings, then doc ids only)
     // page-locked staging buffer of bm25x_batch_prepare (grow-only, shared by the batches of this index)
     uint32_t *h_stage = nullptr;

@@ -34,6 +34,9 @@ struct SearchParams {
     // positions in this launch's query list; resume[position] = the hand-over record
     uint32_t *q2;
     ResumeRec *resume;
+    // champion lists (DeviceIndex::champ): seeded launches (RCfg::SEEDED) take their single-term documents from these
+    const Posting *champ;
+    const uint64_t *champ_off;
     unsigned long long *fetched;        // Σ postings actually loaded into shared memory (pruning statistics)
     uint8_t *pool_scratch;              // k > 1024: per-warp candidate pools in HBM (k_search_ring, RCfg::POOL_GLOBAL)
     int prune;

@@ -225,6 +225,103 @@ __global__ void k_term_ub(const uint64_t *__restrict__ off_pad, const uint32_t *
     }
 }
 
+// Champion lists: one warp per term keeps the best L postings by (exact single-term score desc, doc id asc) — the order in
+// which single-term documents enter a result (Cache::evaluate, bm25.rs:355-358, is the whole score of such a document).
+// The list is scanned once in doc order; a posting is buffered only if it beats the current L-th best (later documents
+// lose ties), and the 2L-entry buffer is sorted and cut back to L when it fills.
+#define CHAMP_WARPS 4
+__global__ void __launch_bounds__(CHAMP_WARPS * 32) k_champions(const uint64_t *__restrict__ off_pad, const uint32_t *__restrict__ df,
+                                                                const Posting *__restrict__ post, const double *__restrict__ s0d,
+                                                                const double *__restrict__ s1d, uint32_t n_terms,
+                                                                const uint64_t *__restrict__ champ_off, Posting *__restrict__ champ) {
+    constexpr int L = (int)BM25X_CHAMP_L, CAP = 2 * L;
+    __shared__ double bs[CHAMP_WARPS][CAP];
+    __shared__ uint32_t bd[CHAMP_WARPS][CAP], bw[CHAMP_WARPS][CAP];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    double *ss = bs[wid];
+    uint32_t *sd = bd[wid], *sw = bw[wid];
+    const uint32_t lt = (1u << lane) - 1u;
+    auto sort_buf = [&](int n) {  // bitonic over CAP entries, best first; entries >= n are padding (score -1)
+        for (int i = n + lane; i < CAP; i += 32) {
+            ss[i] = -1.0;
+            sd[i] = BM25X_DOC_INF;
+            sw[i] = 0;
+        }
+        __syncwarp();
+        for (int size = 2; size <= CAP; size <<= 1)
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                for (int i = lane; i < CAP / 2; i += 32) {
+                    const int a = 2 * i - (i & (stride - 1)), b = a + stride;
+                    const double sa = ss[a], sb = ss[b];
+                    const uint32_t da = sd[a], db = sd[b];
+                    const bool a_first = sa > sb || (sa == sb && da < db);
+                    const bool desc = (a & size) == 0;
+                    if (desc ? !a_first : a_first) {
+                        ss[a] = sb;
+                        ss[b] = sa;
+                        sd[a] = db;
+                        sd[b] = da;
+                        const uint32_t t = sw[a];
+                        sw[a] = sw[b];
+                        sw[b] = t;
+                    }
+                }
+                __syncwarp();
+            }
+    };
+    for (uint32_t t = blockIdx.x * CHAMP_WARPS + wid; t < n_terms; t += gridDim.x * CHAMP_WARPS) {
+        const Posting *pp = post + off_pad[t];
+        const uint32_t n = df[t];
+        const double s0 = s0d[t];
+        int cnt = 0;
+        bool have = false;
+        double thr = 0.0;
+        for (uint32_t base = 0; base < n; base += 32) {
+            const uint32_t i = base + lane;
+            Posting v;
+            v.doc = 0;
+            v.w = 0;
+            double sc = -1.0;
+            if (i < n) {
+                v = pp[i];
+                const double tfd = (double)(v.w >> 8);
+                sc = __ddiv_rn(__dmul_rn(tfd, s0), __dadd_rn(tfd, s1d[v.w & 0xFFu]));
+            }
+            const bool acc = i < n && (!have || sc > thr);
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, acc);
+            if (acc) {
+                const int at = cnt + __popc(m & lt);
+                ss[at] = sc;
+                sd[at] = v.doc;
+                sw[at] = v.w;
+            }
+            cnt += __popc(m);
+            if (cnt > CAP - 32) {
+                __syncwarp();
+                sort_buf(cnt);
+                cnt = L;
+                thr = ss[L - 1];
+                have = true;
+                __syncwarp();
+            }
+        }
+        __syncwarp();
+        sort_buf(cnt);
+        const int keep = cnt < L ? cnt : L;
+        Posting *out = champ + champ_off[t];
+        for (int i = lane; i < keep; i += 32) {
+            Posting v;
+            v.doc = sd[i];
+            v.w = sw[i];
+            out[i] = v;
+        }
+        __syncwarp();
+    }
+}
+
+// champ_off from the host copy of df, then the lists (index_finish_device / finalize_replica; needs post, s0d, s1d)
+static cudaError_t build_champions(bm25x_index *ix);
+
 template <typename T>
 static int dev_alloc(bm25x_index *ix, T **p, size_t n) {
     size_t bytes = sizeof(T) * (n ? n : 1);
@@ -232,6 +329,34 @@ static int dev_alloc(bm25x_index *ix, T **p, size_t n) {
     ix->allocs.push_back((void *)*p);
     ix->device_bytes += bytes;
     return BM25X_OK;
+}
+
+static cudaError_t build_champions(bm25x_index *ix) {
+    DeviceIndex &d = ix->d;
+    const uint32_t T = d.n_terms;
+    std::vector<uint64_t> h_off((size_t)T + 1);
+    uint64_t run = 0;
+    for (uint32_t t = 0; t < T; t++) {
+        h_off[t] = run;
+        run += std::min<uint32_t>(ix->h_df[t], BM25X_CHAMP_L);
+    }
+    h_off[T] = run;
+    d.n_champ = run;
+    cudaError_t e = cudaMalloc((void **)&d.champ, sizeof(Posting) * (size_t)(run ? run : 1));
+    if (e != cudaSuccess) return e;
+    ix->allocs.push_back((void *)d.champ);
+    ix->device_bytes += sizeof(Posting) * (size_t)(run ? run : 1);
+    e = cudaMalloc((void **)&d.champ_off, sizeof(uint64_t) * ((size_t)T + 1));
+    if (e != cudaSuccess) return e;
+    ix->allocs.push_back((void *)d.champ_off);
+    ix->device_bytes += sizeof(uint64_t) * ((size_t)T + 1);
+    e = cudaMemcpy(d.champ_off, h_off.data(), sizeof(uint64_t) * ((size_t)T + 1), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess || !T) return e;
+    const unsigned blocks = (unsigned)std::min<uint64_t>(((uint64_t)T + CHAMP_WARPS - 1) / CHAMP_WARPS, 148ull * 16ull);
+    k_champions<<<blocks, CHAMP_WARPS * 32>>>(d.post_off, d.df, d.post, d.s0d, d.s1d, T, d.champ_off, d.champ);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    return e;
 }
 
 #define TRY(x)                      \
@@ -298,12 +423,20 @@ static int check_keys(const char *who, const uint8_t *term_key, uint32_t T) {
 }
 
 // Allocates the index and fills everything except the postings.  On failure the index is destroyed.
+// Environment overrides of the option defaults (test matrix: BM25X_SEED=0 / BM25X_TWOPHASE=1 run the same tests through
+// the other kernel paths); bm25x_index_set_option still wins.
+static void apply_env_options(bm25x_index *ix) {
+    if (const char *e = getenv("BM25X_SEED")) ix->seed = atoi(e) != 0;
+    if (const char *e = getenv("BM25X_TWOPHASE")) ix->twophase = atoi(e) != 0;
+}
+
 static int index_begin(const BuildMeta &m, int device, bm25x_index **ixp) {
     *ixp = nullptr;
     fn_init();
     const uint32_t N = m.n_docs, T = m.n_terms;
     const uint64_t P = m.n_post;
     bm25x_index *ix = new bm25x_index();
+    apply_env_options(ix);
     ix->device = device;
     ix->k1 = m.k1;
     ix->b = m.b;
@@ -452,6 +585,7 @@ static cudaError_t index_finish_device(bm25x_index *ix) {
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = build_champions(ix);
     return e;
 }
 
@@ -870,6 +1004,7 @@ extern "C" int bm25x_index_alloc_replica(const bm25x_index_layout *like, int dev
         return BM25X_ERR_CUDA;
     }
     bm25x_index *ix = new bm25x_index();
+    apply_env_options(ix);
     ix->device = device;
     ix->k1 = like->k1;
     ix->b = like->b;
@@ -931,6 +1066,7 @@ extern "C" int bm25x_index_finalize_replica(bm25x_index *ix) {
     ix->h_df.resize(ix->d.n_terms);
     if (ix->d.n_terms)
         BM25X_CUDA_TRY(cudaMemcpy(ix->h_df.data(), ix->d.df, sizeof(uint32_t) * ix->d.n_terms, cudaMemcpyDeviceToHost));
+    if (!ix->d.champ) BM25X_CUDA_TRY(build_champions(ix));  // derived data: built here from the replicated arrays
     {   // s1f_min from the replicated arrays (see index_begin)
         std::vector<uint8_t> h_fn(ix->d.n_docs);
         float h_s1f[256];
@@ -953,6 +1089,10 @@ extern "C" int bm25x_index_set_option(bm25x_index *ix, const char *name, int64_t
     }
     if (strcmp(name, "prune") == 0) {
         ix->prune = value != 0;
+        return BM25X_OK;
+    }
+    if (strcmp(name, "seed") == 0) {  // 2..4-term classes: pools seeded from the champion lists, doc-id-only stream
+        ix->seed = value != 0;
         return BM25X_OK;
     }
     if (strcmp(name, "twophase") == 0) {  // 2..4-term classes: 8-byte postings first, doc ids only once no posting passes alone

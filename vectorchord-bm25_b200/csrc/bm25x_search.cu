@@ -109,6 +109,11 @@ int bm25x_launch_ring_kp131072(int device, int sm_count, const SearchParams &sp,
 
 // Two launches per class: 2..4 terms with the pool in shared memory (k <= 224).
 static bool two_phase_class(const bm25x_index *ix, int M, uint32_t k) { return ix->twophase && M >= 2 && M <= 4 && k <= 224; }
+// One seeded launch (phase 3): 2..4 terms, k within the champion lists, no prefilter bitmap (a filtered-out champion would
+// have to be replaced by the next one of its term: such batches take the unseeded kernels).
+static bool seeded_class(const bm25x_index *ix, int M, uint32_t k, const uint8_t *allow) {
+    return ix->seed && ix->d.champ && !allow && M >= 2 && M <= 4 && k <= BM25X_CHAMP_L;
+}
 
 static int launch_ring_k(const bm25x_index *ix, const SearchParams &sp, int M, int phase, cudaStream_t stream) {
     if (sp.k <= 32) return bm25x_launch_ring_kp64(ix->device, ix->sm_count, sp, M, phase, stream);
@@ -416,6 +421,8 @@ extern "C" int bm25x_batch_run(bm25x_batch *b, void *stream_v, bm25x_search_stat
         SearchParams sp;
         sp.post = d.post;
         sp.pdoc = d.pdoc;
+        sp.champ = d.champ;
+        sp.champ_off = d.champ_off;
         sp.post_off = d.post_off;
         sp.df = d.df;
         sp.blk_off = d.blk_off;
@@ -447,7 +454,9 @@ extern "C" int bm25x_batch_run(bm25x_batch *b, void *stream_v, bm25x_search_stat
         sp.q2 = g.d_q2;
         sp.resume = g.d_resume;
         int rc = BM25X_OK;
-        if (g.d_q2 && ix->twophase) {
+        if (seeded_class(ix, g.M, b->k, b->d_allow)) {
+            rc = launch_ring_k(ix, sp, g.M, 3, st);
+        } else if (g.d_q2 && ix->twophase) {
             // first phase: 8-byte postings until no posting can enter the top-k alone; second phase: the suspended
             // queries go on with doc ids only (bm25x_search_ring.cuh, RCfg::PH)
             BM25X_CUDA_TRY(cudaMemsetAsync(g.d_q2, 0, 2 * sizeof(uint32_t), st));

@@ -54,6 +54,12 @@ int BM25X_RING_ENTRY(BM25X_RING_KP)(int device, int sm_count, const SearchParams
             case 4: return launch_ring<RCfg<4, BM25X_RING_KP, 2>>(device, sm_count, sp, stream);
             default: break;
         }
+    if (phase == 3) switch (M) {
+            case 2: return launch_ring<RCfg<2, BM25X_RING_KP, 3>>(device, sm_count, sp, stream);
+            case 3: return launch_ring<RCfg<3, BM25X_RING_KP, 3>>(device, sm_count, sp, stream);
+            case 4: return launch_ring<RCfg<4, BM25X_RING_KP, 3>>(device, sm_count, sp, stream);
+            default: break;
+        }
 #endif
     if (phase != 0) {
         bm25x_set_error("k_search_ring: no two-phase launch for %d terms / pool %d", M, (int)BM25X_RING_KP);

@@ -115,7 +115,10 @@ struct RCfg {
     static constexpr size_t POOL_SMEM = POOL_GLOBAL ? 0 : (size_t)KP_;
     // ring postings per run: half a ring is in flight while the other half is processed
     // doc-id-only rings (2..4 terms): ring element = u32 doc id, the posting word comes from HBM on demand
-    static constexpr bool DOCRING = PH_ == 2 || (PH_ == 0 && (BM25X_DOCRING != 0) && M_ >= 2 && M_ <= 4);
+    static constexpr bool DOCRING = PH_ >= 2 || (PH_ == 0 && (BM25X_DOCRING != 0) && M_ >= 2 && M_ <= 4);
+    // PH_ = 3: one SEEDED launch — the documents that hold a single query term come from the terms' champion lists
+    // (DeviceIndex::champ) before the stream starts, so the stream (doc ids only) never tests a posting on its own
+    static constexpr bool SEEDED = PH_ == 3;
     using RT = typename std::conditional<DOCRING, uint32_t, Posting>::type;  // ring element
     static constexpr uint32_t AL = DOCRING ? 4u : 2u;                        // ring elements per 16 bytes (TMA granularity)
     static constexpr int LOG_R = DOCRING ? BM25X_DOCRING_LOG_R : (BM25X_RING_LOG_R > 0 ? BM25X_RING_LOG_R : (M_ <= 8 ? 8 : 7));
@@ -424,7 +427,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
         float ne_prefix_f = 0.f;   // lane t: Σ bounds of the terms pruned before the t-th one, rounded up
         float FloT = -1.f;         // filter threshold on the score over ALL terms (f.Flo: over the streamed terms only)
         bool thr_new = false;     // the threshold moved since the pruned set was last reconsidered
-        uint32_t wlim = 255u;         // lane j: single-term postings of run j can pass only if w > wlim  (tf >= 1: all)
+        uint32_t wlim = C::SEEDED ? 0xFFFFFFFFu : 255u;  // lane j: single-term postings of run j can pass only if w > wlim  (tf >= 1: all)
 #ifdef BM25X_DIAG_NOSOLO
         wlim = 0xFFFFFFFFu;
 #endif
@@ -456,6 +459,15 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
             wlim = 0xFFFFFFFFu;
 #endif
             tiew = (f.tie_dk != INF && (f.tie_sig >> 27) == (uint32_t)lane) ? (f.tie_sig & 0x07FFFFFFu) : 0xFFFFFFFFu;
+            if constexpr (C::SEEDED) {
+                // single-term documents came from the champion lists: the stream lists no posting on its own — unless
+                // terms are pruned: a document with ONE streamed holder may hold pruned terms too, and the test above (whose
+                // threshold is lowered by the pruned terms' bounds) is what finds it
+                if (ne_mask == 0u) {
+                    wlim = 0xFFFFFFFFu;
+                    tiew = 0xFFFFFFFFu;
+                }
+            }
         };
         // cut the pool back to k and refresh the threshold (Results::push / threshold, search.rs:284-314)
         auto pool_cut = [&]() {
@@ -531,6 +543,70 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
             inflight = issue_round(lane < (int)m && !((ne_mask >> lane) & 1u) ? min(rsize, dfpad - wr) : 0u);
         } else {
             inflight = issue_round(lane < (int)m ? min(dfpad, (uint32_t)C::INIT) : 0u);
+        }
+        if constexpr (C::SEEDED) {
+            // ---- seed (while the first round is in flight): a document that holds ONE query term can only be in the top-k
+            // if it is among the first k champions of that term — every posting ranked before it in (single-term score
+            // desc, doc asc) belongs to a document that beats it.  So: the first min(k, df) champions of every term, 32 at
+            // a time; the other terms are probed in HBM (block table, then inside the block); champions that hold another
+            // query term are left to the stream (it finds every such document with its full score), the others enter the
+            // pool with their exact score.  The stream then never tests a posting on its own.
+            uint32_t ncj = 0u;
+            uint64_t coff = 0ull;
+            if (lane < (int)m) {
+                ncj = min(dfj, min(k, (uint32_t)BM25X_CHAMP_L));
+                coff = p.champ_off[p.q_terms[t0 + lane]];
+            }
+            uint32_t cincl = ncj;
+#pragma unroll
+            for (int o = 1; o < C::M; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(FULL, cincl, o);
+                if (lane >= o) cincl += v;
+            }
+            const uint32_t ctotal = __shfl_sync(FULL, cincl, C::M - 1);
+            for (uint32_t base = 0; base < ctotal; base += 32) {
+                const uint32_t c = base + lane;
+                const bool has = c < ctotal;
+                uint32_t j = 0u, start = 0u;
+#pragma unroll
+                for (int jj = 0; jj < C::M - 1; ++jj) {
+                    const uint32_t cj = __shfl_sync(FULL, cincl, jj);
+                    if (c >= cj) {
+                        j = (uint32_t)jj + 1u;
+                        start = cj;
+                    }
+                }
+                const uint64_t cof = __shfl_sync(FULL, coff, j);
+                Posting ch;
+                ch.doc = 0u;
+                ch.w = 0u;
+                if (has) ch = p.champ[cof + (c - start)];
+                bool single = has;
+#pragma unroll
+                for (int i = 0; i < C::M; ++i) {
+                    const uint64_t pbi = __shfl_sync(FULL, pbase, i), bbi = __shfl_sync(FULL, bbase, i);
+                    const uint32_t nbi = __shfl_sync(FULL, nbj, i), dfi = __shfl_sync(FULL, dfj, i);
+                    if (i < (int)m && single && (uint32_t)i != j) {
+                        const uint32_t l = probe_block(p, bbi, nbi, ch.doc, probe_steps);
+                        if (l > 0u && probe_in_block(p, pbi, dfi, l - 1u, ch.doc, probe_steps) != 0u) single = false;
+                    }
+                }
+                const double s0j = __shfl_sync(FULL, s0d, j);
+                double Sx = 0.0;
+                if (single) Sx = __dadd_rn(0.0, score_f64(ch.w, s0j, p.s1d));
+                const bool keep = single && (!f.tv || Sx > f.Sk || (Sx == f.Sk && ch.doc < f.dk));
+                const uint32_t mk = __ballot_sync(FULL, keep);
+                if (keep) {
+                    const int idx = pn + __popc(mk & lt_mask);
+                    pl.s[idx] = (uint64_t)__double_as_longlong(Sx);
+                    pl.d[idx] = ch.doc;
+                    pl.g[idx] = make_sig(j, ch.w);
+                }
+                pn += __popc(mk);
+                __syncwarp();
+                if (pn > C::KP - 32 || pn >= (int)k + 32) pool_cut();
+            }
+            if (pn > 0) pool_cut();
         }
 #ifdef BM25X_WATCHDOG
         uint32_t wd_chunks = 0;
@@ -705,6 +781,8 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                         const uint32_t raj = __shfl_sync(FULL, rd, j & 31u);
                         const uint64_t pbj = __shfl_sync(FULL, pbase, j & 31u);
                         solo_j = __shfl_sync(FULL, wlim, j & 31u) != 0xFFFFFFFFu;
+                        // seeded launch: a lone streamed holder only matters when a pruned term may hold the document too
+                        if constexpr (C::SEEDED) solo_j = solo_j || ne_mask != 0u;
                         if (has && !by_doc) {
                             const uint32_t pos = ent & 0x3FFu;
                             own.doc = rings[jbase + pos];
@@ -786,6 +864,8 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                             }
                             wv[i] = has ? wi : 0u;
                         }
+                        // seeded launch: single-term documents are in the pool already (or lost to better ones)
+                        if constexpr (C::SEEDED) has = has && !(ne_mask == 0u && cnt == 1u);
                     } else if (C::M == 3 && pairs) {
                         if constexpr (C::M == 3) {
                             // my run to search: the first (even lane) or second (odd lane) of the two runs other than j
@@ -925,6 +1005,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                             }
                         }
                         keep = keep && (!f.tv || Sx > f.Sk || (Sx == f.Sk && doc < f.dk));
+                        if constexpr (C::SEEDED) keep = keep && cnt_all != 1u;  // (its only holder is a streamed term after all)
                         const uint32_t mk = __ballot_sync(FULL, keep);
                         if (keep) {
                             const int idx = pn + __popc(mk & lt_mask);
