@@ -92,6 +92,9 @@ namespace {
 #define BM25X_RING_K2 1  // bit map only: TWO bits per document inside one 32-bit cell word (blocked Bloom filter, one
                          // shared-memory atomicOr / one load as before): false alarms ~ (fill)^2 instead of fill
 #endif
+#ifndef BM25X_SEED_INIT_FULL
+#define BM25X_SEED_INIT_FULL 1
+#endif
 #ifndef BM25X_SUSPEND_MIN
 #define BM25X_SUSPEND_MIN 4096  // first phase: a query is handed to the doc-id-only phase when at least this many postings remain
 #endif
@@ -154,7 +157,11 @@ struct RCfg {
     static constexpr size_t off_pool_d = off_pool_s + POOL_SMEM * 8;
     static constexpr size_t off_pool_g = off_pool_d + POOL_SMEM * 4;
     static constexpr size_t off_cand = off_pool_g + POOL_SMEM * 4;
-    static constexpr size_t off_bar = (off_cand + (size_t)LCAP * 2 + 7) & ~(size_t)7;
+    // seeded launches: the first k champions of the query's terms (doc, w) in shared memory, SST slots per term
+    static constexpr uint32_t SST = KP_ <= 64 ? 32u : 128u;
+    static constexpr bool SEEDS_SMEM = SEEDED;
+    static constexpr size_t off_seed = (off_cand + (size_t)LCAP * 2 + 7) & ~(size_t)7;
+    static constexpr size_t off_bar = off_seed + (SEEDS_SMEM ? (size_t)M_ * SST * 8 : 0);
     static constexpr size_t warp_bytes = (off_bar + 8 + 127) & ~(size_t)127;
     static constexpr size_t off_s1f = 0;  // CTA-shared: 1 KiB table first, then the warps
     static constexpr size_t shared_bytes = 1024;
@@ -542,71 +549,39 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
             wr = rd & ~(C::AL - 1u);
             inflight = issue_round(lane < (int)m && !((ne_mask >> lane) & 1u) ? min(rsize, dfpad - wr) : 0u);
         } else {
-            inflight = issue_round(lane < (int)m ? min(dfpad, (uint32_t)C::INIT) : 0u);
+            // (a seeded launch needs no early threshold: whole rings from the start)
+            inflight = issue_round(lane < (int)m ? min(dfpad, C::SEEDED && BM25X_SEED_INIT_FULL ? rsize : (uint32_t)C::INIT) : 0u);
         }
+        // ---- seeds: a document that holds ONE query term can only be in the top-k if it is among the first k champions
+        // of that term (DeviceIndex::champ: every posting ranked before it in (single-term score desc, doc asc) belongs
+        // to a document that beats it).  The first min(k, df) champions of every term are the query's seeds; each is
+        // handed to the verification of the doc window it falls into (the rings then hold every other run's postings of
+        // that window): a seed no other term holds enters the pool with its exact score, the others are left to the
+        // stream, which finds every document held by two terms.  The stream itself never tests a posting on its own.
+        uint32_t ncj = 0u;    // lane j: seeds of term j
+        uint64_t coff = 0ull;  // lane j: its champion list
+        [[maybe_unused]] Posting *seeds = nullptr;
         if constexpr (C::SEEDED) {
-            // ---- seed (while the first round is in flight): a document that holds ONE query term can only be in the top-k
-            // if it is among the first k champions of that term — every posting ranked before it in (single-term score
-            // desc, doc asc) belongs to a document that beats it.  So: the first min(k, df) champions of every term, 32 at
-            // a time; the other terms are probed in HBM (block table, then inside the block); champions that hold another
-            // query term are left to the stream (it finds every such document with its full score), the others enter the
-            // pool with their exact score.  The stream then never tests a posting on its own.
-            uint32_t ncj = 0u;
-            uint64_t coff = 0ull;
             if (lane < (int)m) {
                 ncj = min(dfj, min(k, (uint32_t)BM25X_CHAMP_L));
                 coff = p.champ_off[p.q_terms[t0 + lane]];
             }
-            uint32_t cincl = ncj;
+            if constexpr (C::SEEDS_SMEM) {
+                seeds = (Posting *)(ws + C::off_seed);
 #pragma unroll
-            for (int o = 1; o < C::M; o <<= 1) {
-                const uint32_t v = __shfl_up_sync(FULL, cincl, o);
-                if (lane >= o) cincl += v;
-            }
-            const uint32_t ctotal = __shfl_sync(FULL, cincl, C::M - 1);
-            for (uint32_t base = 0; base < ctotal; base += 32) {
-                const uint32_t c = base + lane;
-                const bool has = c < ctotal;
-                uint32_t j = 0u, start = 0u;
-#pragma unroll
-                for (int jj = 0; jj < C::M - 1; ++jj) {
-                    const uint32_t cj = __shfl_sync(FULL, cincl, jj);
-                    if (c >= cj) {
-                        j = (uint32_t)jj + 1u;
-                        start = cj;
+                for (int jj = 0; jj < C::M; ++jj) {
+                    const uint32_t nj = __shfl_sync(FULL, ncj, jj);
+                    const uint64_t cj = __shfl_sync(FULL, coff, jj);
+                    for (uint32_t r = (uint32_t)lane; r < C::SST && r < ((k + 31u) & ~31u); r += 32) {
+                        Posting v;
+                        v.doc = INF;  // slots beyond the list: never inside a window
+                        v.w = 0u;
+                        if (r < nj) v = p.champ[cj + r];
+                        seeds[jj * C::SST + r] = v;
                     }
                 }
-                const uint64_t cof = __shfl_sync(FULL, coff, j);
-                Posting ch;
-                ch.doc = 0u;
-                ch.w = 0u;
-                if (has) ch = p.champ[cof + (c - start)];
-                bool single = has;
-#pragma unroll
-                for (int i = 0; i < C::M; ++i) {
-                    const uint64_t pbi = __shfl_sync(FULL, pbase, i), bbi = __shfl_sync(FULL, bbase, i);
-                    const uint32_t nbi = __shfl_sync(FULL, nbj, i), dfi = __shfl_sync(FULL, dfj, i);
-                    if (i < (int)m && single && (uint32_t)i != j) {
-                        const uint32_t l = probe_block(p, bbi, nbi, ch.doc, probe_steps);
-                        if (l > 0u && probe_in_block(p, pbi, dfi, l - 1u, ch.doc, probe_steps) != 0u) single = false;
-                    }
-                }
-                const double s0j = __shfl_sync(FULL, s0d, j);
-                double Sx = 0.0;
-                if (single) Sx = __dadd_rn(0.0, score_f64(ch.w, s0j, p.s1d));
-                const bool keep = single && (!f.tv || Sx > f.Sk || (Sx == f.Sk && ch.doc < f.dk));
-                const uint32_t mk = __ballot_sync(FULL, keep);
-                if (keep) {
-                    const int idx = pn + __popc(mk & lt_mask);
-                    pl.s[idx] = (uint64_t)__double_as_longlong(Sx);
-                    pl.d[idx] = ch.doc;
-                    pl.g[idx] = make_sig(j, ch.w);
-                }
-                pn += __popc(mk);
                 __syncwarp();
-                if (pn > C::KP - 32 || pn >= (int)k + 32) pool_cut();
             }
-            if (pn > 0) pool_cut();
         }
 #ifdef BM25X_WATCHDOG
         uint32_t wd_chunks = 0;
@@ -768,7 +743,10 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                     bool has = ci < nc;
                     const uint32_t ent = has ? cand[ci] : 0u;
                     const bool by_doc = (ent >> 15) != 0u;            // dense flavour: document given as offset from lo
-                    const uint32_t j = by_doc ? 32u : (ent >> 10) & 31u;
+                    // seeded launches: run field 31 = a seed (champion of term sidx / SST, slot sidx % SST)
+                    const bool is_seed = C::SEEDED && has && !by_doc && ((ent >> 10) & 31u) == 31u;
+                    const uint32_t sidx = ent & 0x3FFu;
+                    const uint32_t j = by_doc ? 32u : (is_seed ? sidx / C::SST : (ent >> 10) & 31u);
                     Posting own;
                     own.doc = 0;
                     own.w = 0;
@@ -783,7 +761,13 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                         solo_j = __shfl_sync(FULL, wlim, j & 31u) != 0xFFFFFFFFu;
                         // seeded launch: a lone streamed holder only matters when a pruned term may hold the document too
                         if constexpr (C::SEEDED) solo_j = solo_j || ne_mask != 0u;
-                        if (has && !by_doc) {
+                        if constexpr (C::SEEDS_SMEM) {
+                            if (is_seed) own = seeds[sidx];
+                        } else if constexpr (C::SEEDED) {
+                            const uint64_t cjs = __shfl_sync(FULL, coff, j & 31u);
+                            if (is_seed) own = p.champ[cjs + (sidx % C::SST)];
+                        }
+                        if (has && !by_doc && !is_seed) {
                             const uint32_t pos = ent & 0x3FFu;
                             own.doc = rings[jbase + pos];
                             gown = p.post + pbj + (raj + ((pos - raj) & ((uint32_t)C::R - 1u)));
@@ -848,7 +832,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                                 }
                             }
                         }
-                        if (!by_doc) {
+                        if (!by_doc && !is_seed) {
                             has = has && (found || solo_j);  // a lone posting of a run that cannot pass alone: dropped unread
                             if (has) own.w = __ldg(&gown->w);
                         }
@@ -865,7 +849,9 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                             wv[i] = has ? wi : 0u;
                         }
                         // seeded launch: single-term documents are in the pool already (or lost to better ones)
-                        if constexpr (C::SEEDED) has = has && !(ne_mask == 0u && cnt == 1u);
+                        // (a seed that another term holds is the stream's business; a streamed posting that no other term
+                        // holds is a seed's)
+                        if constexpr (C::SEEDED) has = has && (is_seed ? cnt == 1u : !(ne_mask == 0u && cnt == 1u));
                     } else if (C::M == 3 && pairs) {
                         if constexpr (C::M == 3) {
                             // my run to search: the first (even lane) or second (odd lane) of the two runs other than j
@@ -1005,7 +991,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                             }
                         }
                         keep = keep && (!f.tv || Sx > f.Sk || (Sx == f.Sk && doc < f.dk));
-                        if constexpr (C::SEEDED) keep = keep && cnt_all != 1u;  // (its only holder is a streamed term after all)
+                        if constexpr (C::SEEDED) keep = keep && (is_seed ? cnt_all == 1u : cnt_all != 1u);  // (pruned terms probed)
                         const uint32_t mk = __ballot_sync(FULL, keep);
                         if (keep) {
                             const int idx = pn + __popc(mk & lt_mask);
@@ -1024,6 +1010,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                 __syncwarp();  // every lane has read its entries before the producers refill the list
                 nc = 0;
             };
+
 
             // Classes of 8+ terms unite a few thousand postings per chunk: the presence map would be a quarter full and a
             // tenth of all postings false alarms.  The chunk is therefore walked in doc SUB-WINDOWS of about SUBT postings,
@@ -1046,6 +1033,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
             // memory; docs are distinct inside a run: plain read-modify-write, __syncwarp between runs), then scanned.
             uint32_t todo = 0u, ra = 0u, ree = 0u, rnj = 0u, wl = 0u, tw = 0u, tdk = 0u, pb = 0u, genv = 0u, dbase = 0u, rm = 1u;
             int rj = -1, variant = 0;
+            uint32_t ss = 0u;  // seeded launches: next slice (term, 32 slots) of the seed table to look at in this window
             bool multi = false;
             const uint4 *rg = nullptr;
             const uint4 *gq = nullptr;  // DOCRING: the current run's 8-byte postings in HBM (single-term test only)
@@ -1175,7 +1163,32 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
             // window is done; ONE verification site after it.
             bool more = true;
             while (more) {
-                if (!dense) {
+                bool seeds_pending = false;
+                if constexpr (C::SEEDED) {
+                    // the seeds of this doc window join the candidate list first (entry: run field 31 | seed slot); the
+                    // rings hold every run's postings of the window, so the ONE verification site below tells whether
+                    // another term holds the document
+#ifdef BM25X_DIAG_NOSEEDS  // timing diagnostics only (wrong results): the seeds never join
+                    const uint32_t slices = 0u;
+#else
+                    const uint32_t slices = (min(k, (uint32_t)BM25X_CHAMP_L) + 31u) >> 5;  // per term
+#endif
+#pragma unroll 1
+                    while (ss < (uint32_t)C::M * slices && nc <= 64u) {
+                        const uint32_t jj = ss / slices, r = (ss % slices) * 32u + (uint32_t)lane;
+                        ++ss;
+                        if (jj >= m || ((ne_mask >> jj) & 1u)) continue;  // a pruned term's documents cannot enter
+                        const uint32_t d = seeds[jj * C::SST + r].doc;
+                        const bool inw = d >= lo && d < hi;
+                        const uint32_t bal = __ballot_sync(FULL, inw);
+                        if (inw) cand[nc + __popc(bal & lt_mask)] = (uint16_t)((31u << 10) | (jj * C::SST + r));
+                        nc += __popc(bal);
+                    }
+                    seeds_pending = ss < (uint32_t)C::M * slices;
+                }
+                if (seeds_pending) {
+                    __syncwarp();  // list full: verify, then go on with the seeds
+                } else if (!dense) {
                     for (;;) {
                         if (pb >= ree) {  // next run
                             if (rj >= 0) __syncwarp();  // this run's marks are visible to the next run's tests
