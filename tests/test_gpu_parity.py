@@ -144,11 +144,14 @@ def test_kernel_paths_identical(m, orc, zipf):
         for prune in (1, 0):
             ix.set_option("prune", prune)
             got = {}
-            for name, (seed, two) in dict(seeded=(1, 0), twophase=(0, 1), plain=(0, 0)).items():
+            for name, (seed, two, spm) in dict(seeded=(1, 0, 1 << 30), handback=(1, 0, 64), twophase=(0, 1, 0),
+                                               plain=(0, 0, 0)).items():
                 ix.set_option("seed", seed)
                 ix.set_option("twophase", two)
+                # seeded launches hand skewed queries (a list >= this long and 8x the shortest) back to the pruning kernel
+                ix.set_option("seed_prune_min", spm)
                 got[name] = ix.search_batch(q_off, q_terms, k)
-            for name in ("seeded", "twophase"):
+            for name in ("seeded", "handback", "twophase"):
                 for key in ("doc", "score", "score64", "n"):
                     assert np.array_equal(got[name][key], got["plain"][key]), (name, key, k, prune)
         _compare(got["seeded"], oix, q_off[:25], q_terms, k, what=f"paths k={k}")

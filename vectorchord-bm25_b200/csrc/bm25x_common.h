@@ -17,6 +17,9 @@
 #define BM25X_CHAMP_L 128u          // champion list: the best min(df, 128) postings of every term by single-term score
 #define BM25X_POST_SLACK 4u         // slack slots behind the last list, reading as exhausted cursors
 
+#ifndef BM25X_SEED_MAX_TERMS
+#define BM25X_SEED_MAX_TERMS 8
+#endif
 #ifndef BM25X_TWOPHASE_DEFAULT
 #define BM25X_TWOPHASE_DEFAULT 0
 #endif
@@ -87,6 +90,8 @@ struct bm25x_index {
     cudaStream_t stream = nullptr;
     std::vector<void *> allocs;
     int prune = 1;                     // MaxScore-style pruning in the search kernels
+    uint32_t seed_prune_min = 32768;   // seeded launches hand queries with a list this long (and 8x their shortest) to the pruning kernel
+    int seed_max_terms = BM25X_SEED_MAX_TERMS;  // widest term-count class that runs seeded (4 or 8)
     int seed = 1;                      // 2..4-term classes, k <= BM25X_CHAMP_L, no prefilter: pools seeded from the champion lists
     int twophase = BM25X_TWOPHASE_DEFAULT;  // 2..4-term classes, k <= 224: two launches (8-byte postings, then doc ids only)
     // page-locked staging buffer of bm25x_batch_prepare (grow-only, shared by the batches of this index)

@@ -1095,6 +1095,14 @@ extern "C" int bm25x_index_set_option(bm25x_index *ix, const char *name, int64_t
         ix->seed = value != 0;
         return BM25X_OK;
     }
+    if (strcmp(name, "seed_prune_min") == 0) {  // seeded launches: list length from which a skewed query goes to the pruning kernel
+        ix->seed_prune_min = value < 0 ? 0u : (value > 0xFFFFFFFFll ? 0xFFFFFFFFu : (uint32_t)value);
+        return BM25X_OK;
+    }
+    if (strcmp(name, "seed_max_terms") == 0) {  // widest term-count class that runs seeded: 4 or 8
+        ix->seed_max_terms = value >= 8 ? 8 : 4;
+        return BM25X_OK;
+    }
     if (strcmp(name, "twophase") == 0) {  // 2..4-term classes: 8-byte postings first, doc ids only once no posting passes alone
         ix->twophase = value != 0;
         return BM25X_OK;

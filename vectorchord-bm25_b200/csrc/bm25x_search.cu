@@ -112,7 +112,7 @@ static bool two_phase_class(const bm25x_index *ix, int M, uint32_t k) { return i
 // One seeded launch (phase 3): 2..4 terms, k within the champion lists, no prefilter bitmap (a filtered-out champion would
 // have to be replaced by the next one of its term: such batches take the unseeded kernels).
 static bool seeded_class(const bm25x_index *ix, int M, uint32_t k, const uint8_t *allow) {
-    return ix->seed && ix->d.champ && !allow && M >= 2 && M <= 4 && k <= BM25X_CHAMP_L;
+    return ix->seed && ix->d.champ && !allow && M >= 2 && M <= ix->seed_max_terms && k <= BM25X_CHAMP_L;
 }
 
 static int launch_ring_k(const bm25x_index *ix, const SearchParams &sp, int M, int phase, cudaStream_t stream) {
@@ -367,7 +367,7 @@ extern "C" int bm25x_batch_prepare(bm25x_index *ix, uint32_t nq, const uint32_t 
     }
     for (int c = 0; c < kNumClasses; ++c) {
         Group &g = b->groups[c];
-        if (g.nq && two_phase_class(ix, g.M, k)) {
+        if (g.nq && (two_phase_class(ix, g.M, k) || seeded_class(ix, g.M, k, allow))) {
             BTRY(batch_alloc(b, &g.d_q2, (size_t)g.nq + 2));
             BTRY(batch_alloc(b, &g.d_resume, (size_t)g.nq));
         }
@@ -423,6 +423,7 @@ extern "C" int bm25x_batch_run(bm25x_batch *b, void *stream_v, bm25x_search_stat
         sp.pdoc = d.pdoc;
         sp.champ = d.champ;
         sp.champ_off = d.champ_off;
+        sp.seed_prune_min = ix->seed_prune_min;
         sp.post_off = d.post_off;
         sp.df = d.df;
         sp.blk_off = d.blk_off;
@@ -454,8 +455,14 @@ extern "C" int bm25x_batch_run(bm25x_batch *b, void *stream_v, bm25x_search_stat
         sp.q2 = g.d_q2;
         sp.resume = g.d_resume;
         int rc = BM25X_OK;
-        if (seeded_class(ix, g.M, b->k, b->d_allow)) {
+        if (g.d_q2 && seeded_class(ix, g.M, b->k, b->d_allow)) {
+            // seeded launch (champion lists + doc-id-only stream, no pruning); the queries it hands back (a list much
+            // longer than another: pruning pays) go through the plain kernel
+            BM25X_CUDA_TRY(cudaMemsetAsync(g.d_q2, 0, 2 * sizeof(uint32_t), st));
             rc = launch_ring_k(ix, sp, g.M, 3, st);
+            if (rc != BM25X_OK) return rc;
+            launches++;
+            rc = launch_ring_k(ix, sp, g.M, 4, st);
         } else if (g.d_q2 && ix->twophase) {
             // first phase: 8-byte postings until no posting can enter the top-k alone; second phase: the suspended
             // queries go on with doc ids only (bm25x_search_ring.cuh, RCfg::PH)

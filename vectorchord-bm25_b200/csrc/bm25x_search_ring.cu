@@ -58,6 +58,14 @@ int BM25X_RING_ENTRY(BM25X_RING_KP)(int device, int sm_count, const SearchParams
             case 2: return launch_ring<RCfg<2, BM25X_RING_KP, 3>>(device, sm_count, sp, stream);
             case 3: return launch_ring<RCfg<3, BM25X_RING_KP, 3>>(device, sm_count, sp, stream);
             case 4: return launch_ring<RCfg<4, BM25X_RING_KP, 3>>(device, sm_count, sp, stream);
+            case 8: return launch_ring<RCfg<8, BM25X_RING_KP, 3>>(device, sm_count, sp, stream);
+            default: break;
+        }
+    if (phase == 4) switch (M) {
+            case 2: return launch_ring<RCfg<2, BM25X_RING_KP, 4>>(device, sm_count, sp, stream);
+            case 3: return launch_ring<RCfg<3, BM25X_RING_KP, 4>>(device, sm_count, sp, stream);
+            case 4: return launch_ring<RCfg<4, BM25X_RING_KP, 4>>(device, sm_count, sp, stream);
+            case 8: return launch_ring<RCfg<8, BM25X_RING_KP, 4>>(device, sm_count, sp, stream);
             default: break;
         }
 #endif

@@ -83,7 +83,7 @@ namespace {
 #define BM25X_DOCRING_G 1  // 16-byte shared loads (4 doc ids) per lane and trip of a DOCRING class
 #endif
 #ifndef BM25X_DOCRING_TMAX
-#define BM25X_DOCRING_TMAX 3  // trips between two compactions of the detected postings of a DOCRING class
+#define BM25X_DOCRING_TMAX 4  // trips between two compactions of the detected postings of a DOCRING class
 #endif
 #ifndef BM25X_DOCRING_LOG_S
 #define BM25X_DOCRING_LOG_S 11  // log2 of the presence map bytes of a DOCRING class
@@ -110,7 +110,8 @@ template <int M_, int KP_, int PH_ = 0>
 struct RCfg {
     static constexpr int M = M_;    // max live terms (lanes 0..M-1 own the terms)
     static constexpr int PH = PH_;
-    static_assert(PH_ == 0 || (M_ >= 2 && M_ <= 4 && KP_ <= 256), "two-phase launches: 2..4 terms, pools in shared memory");
+    static_assert(PH_ == 0 || (M_ >= 2 && M_ <= 8 && KP_ <= 256), "phased launches: 2..8 terms, pools in shared memory");
+    static_assert((PH_ != 1 && PH_ != 2) || M_ <= 4, "two-phase hand-over record: 4 runs");
     static constexpr int KP = KP_;  // pool capacity (power of two >= k + 32)
     // pools beyond 2048 entries (k > 1024, up to the reference's bm25.limit maximum of 65535, src/index/gucs.rs:37-46)
     // live in HBM: one KP-entry slice of SearchParams::pool_scratch per warp
@@ -118,9 +119,13 @@ struct RCfg {
     static constexpr size_t POOL_SMEM = POOL_GLOBAL ? 0 : (size_t)KP_;
     // ring postings per run: half a ring is in flight while the other half is processed
     // doc-id-only rings (2..4 terms): ring element = u32 doc id, the posting word comes from HBM on demand
-    static constexpr bool DOCRING = PH_ >= 2 || (PH_ == 0 && (BM25X_DOCRING != 0) && M_ >= 2 && M_ <= 4);
+    static constexpr bool DOCRING = PH_ == 2 || PH_ == 3 || (PH_ == 0 && (BM25X_DOCRING != 0) && M_ >= 2 && M_ <= 4);
+    // PH_ = 4: the plain kernel (as PH_ = 0) over the queries a seeded launch handed back (SearchParams::q2)
+    static constexpr bool FROM_Q2 = PH_ == 2 || PH_ == 4;
     // PH_ = 3: one SEEDED launch — the documents that hold a single query term come from the terms' champion lists
     // (DeviceIndex::champ) before the stream starts, so the stream (doc ids only) never tests a posting on its own
+    // A seeded launch never prunes terms (no single-posting test, no probes: a leaner loop) — queries that would gain
+    // from pruning (one list much longer than another) are handed back for the plain kernel (PH_ = 4).
     static constexpr bool SEEDED = PH_ == 3;
     using RT = typename std::conditional<DOCRING, uint32_t, Posting>::type;  // ring element
     static constexpr uint32_t AL = DOCRING ? 4u : 2u;                        // ring elements per 16 bytes (TMA granularity)
@@ -135,7 +140,7 @@ struct RCfg {
     static constexpr bool ADAPT = (BM25X_RING_ADAPT != 0) && M_ >= 8;
     static constexpr int LOG_RMIN = 6;
     static constexpr int LOG_RMAX = (LOG_R + 2 > 10 ? 10 : LOG_R + 2) > LOG_R ? (LOG_R + 2 > 10 ? 10 : LOG_R + 2) : LOG_R;
-    static constexpr int LOG_S = M_ == 1 ? 8 : DOCRING ? BM25X_DOCRING_LOG_S : (BM25X_RING_LOG_S > 0 ? BM25X_RING_LOG_S : (BM25X_RING_BITMAP && M_ <= 4 ? 11 : 13));  // presence map bytes = dense accumulator bytes (unused for one term)
+    static constexpr int LOG_S = M_ == 1 ? 8 : (DOCRING && M_ <= 4) ? BM25X_DOCRING_LOG_S : (BM25X_RING_LOG_S > 0 ? BM25X_RING_LOG_S : (BM25X_RING_BITMAP && M_ <= 4 ? 11 : 13));  // presence map bytes = dense accumulator bytes (unused for one term)
     static constexpr uint32_t MAP_BYTES = M_ == 1 ? 256u : (BM25X_RING_MAPBYTES ? (uint32_t)BM25X_RING_MAPBYTES : (1u << LOG_S));
     static constexpr uint32_t ACC_DOCS = MAP_BYTES / 4u;
     static constexpr int U = DOCRING ? BM25X_DOCRING_G : BM25X_RING_U;  // 16-byte shared loads per lane and trip
@@ -285,7 +290,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
 
     for (;;) {
         int qi = 0;
-        if constexpr (C::PH == 2) {  // the suspended queries of the first phase, in the order they were handed over
+        if constexpr (C::FROM_Q2) {  // the queries another launch handed over (suspended / handed back), in that order
             if (lane == 0) {
                 const uint32_t i = atomicAdd(&p.q2[1], 1u);
                 qi = i < p.q2[0] ? (int)p.q2[2u + i] : -1;
@@ -305,6 +310,21 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
         // documents that hold no group-0 term.  Every document is emitted once, with its full score; pool and threshold
         // span the passes.
         const bool mp = C::M == 32 && m_total > 32u;
+        if constexpr (C::SEEDED) {
+            // MaxScore pruning pays when one list is much longer than another (head term next to rare ones): such a
+            // query goes back to the plain kernel, which prunes
+            uint32_t dfl = 0u;
+            if (lane < (int)m_total) dfl = p.df[p.q_terms[t0q + lane]];
+            const uint32_t mx = __reduce_max_sync(FULL, dfl);
+            const uint32_t mn = __reduce_min_sync(FULL, lane < (int)m_total ? dfl : 0xFFFFFFFFu);
+            if (p.prune && mx >= p.seed_prune_min && mx / 8u >= mn) {
+                if (lane == 0) {
+                    const uint32_t at = atomicAdd(&p.q2[0], 1u);
+                    p.q2[2u + at] = (uint32_t)qi;
+                }
+                continue;
+            }
+        }
         unsigned long long fetched = 0;
         uint32_t probe_steps = 0;
         // per-query pool / threshold state (warp-uniform registers)
@@ -466,14 +486,9 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
             wlim = 0xFFFFFFFFu;
 #endif
             tiew = (f.tie_dk != INF && (f.tie_sig >> 27) == (uint32_t)lane) ? (f.tie_sig & 0x07FFFFFFu) : 0xFFFFFFFFu;
-            if constexpr (C::SEEDED) {
-                // single-term documents came from the champion lists: the stream lists no posting on its own — unless
-                // terms are pruned: a document with ONE streamed holder may hold pruned terms too, and the test above (whose
-                // threshold is lowered by the pruned terms' bounds) is what finds it
-                if (ne_mask == 0u) {
-                    wlim = 0xFFFFFFFFu;
-                    tiew = 0xFFFFFFFFu;
-                }
+            if constexpr (C::SEEDED) {  // single-term documents come from the champion lists: the stream lists no posting on its own
+                wlim = 0xFFFFFFFFu;
+                tiew = 0xFFFFFFFFu;
             }
         };
         // cut the pool back to k and refresh the threshold (Results::push / threshold, search.rs:284-314)
@@ -602,7 +617,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
             // the block-level bound (SummaryTuple.wand_*, search.rs:193-203) of the probed term plus the bounds of the
             // terms still to probe cannot lift it over the threshold.
             // Only at chunk boundaries: inside a chunk the "last holder emits" rule relies on a fixed streamed set.
-            if (p.prune && thr_new) {
+            if (!C::SEEDED && p.prune && thr_new) {
                 thr_new = false;
                 bool changed = false;
                 for (;;) {
@@ -760,17 +775,18 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                         const uint64_t pbj = __shfl_sync(FULL, pbase, j & 31u);
                         solo_j = __shfl_sync(FULL, wlim, j & 31u) != 0xFFFFFFFFu;
                         // seeded launch: a lone streamed holder only matters when a pruned term may hold the document too
-                        if constexpr (C::SEEDED) solo_j = solo_j || ne_mask != 0u;
+                        if constexpr (C::SEEDED) solo_j = false;
                         if constexpr (C::SEEDS_SMEM) {
                             if (is_seed) own = seeds[sidx];
                         } else if constexpr (C::SEEDED) {
                             const uint64_t cjs = __shfl_sync(FULL, coff, j & 31u);
                             if (is_seed) own = p.champ[cjs + (sidx % C::SST)];
                         }
+                        const uint32_t rmj = C::ADAPT ? __shfl_sync(FULL, rmask, j & 31u) : (uint32_t)C::R - 1u;
                         if (has && !by_doc && !is_seed) {
                             const uint32_t pos = ent & 0x3FFu;
                             own.doc = rings[jbase + pos];
-                            gown = p.post + pbj + (raj + ((pos - raj) & ((uint32_t)C::R - 1u)));
+                            gown = p.post + pbj + (raj + ((pos - raj) & rmj));
                         }
                     } else {
                         if (has && !by_doc) own = rings[jbase + (ent & 0x3FFu)];
@@ -826,8 +842,10 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                             for (int i = 0; i < C::M; ++i) {
                                 const uint32_t ai = __shfl_sync(FULL, rd, i), ei = __shfl_sync(FULL, e, i);
                                 const uint64_t pbi = __shfl_sync(FULL, pbase, i);
+                                const uint32_t ib = ring_base(i), im = ring_mask(i);
                                 if (i < (int)m && has && (uint32_t)i != j && !((ne_mask >> i) & 1u)) {
-                                    wv[i] = ring_find<C, C::LOG_R>(rings + i * C::R, C::R - 1u, ai, ei, doc, p.post + pbi);
+                                    wv[i] = small_rings ? ring_find<C, C::LOG_R>(rings + ib, im, ai, ei, doc, p.post + pbi)
+                                                        : ring_find<C>(rings + ib, im, ai, ei, doc, p.post + pbi);
                                     found = found || wv[i] != 0u;
                                 }
                             }
@@ -1033,7 +1051,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
             // memory; docs are distinct inside a run: plain read-modify-write, __syncwarp between runs), then scanned.
             uint32_t todo = 0u, ra = 0u, ree = 0u, rnj = 0u, wl = 0u, tw = 0u, tdk = 0u, pb = 0u, genv = 0u, dbase = 0u, rm = 1u;
             int rj = -1, variant = 0;
-            uint32_t ss = 0u;  // seeded launches: next slice (term, 32 slots) of the seed table to look at in this window
+            uint32_t ss = sub == 0u ? 0u : 0xFFFFFFFFu;  // seeded launches: next slice (term, 32 slots) of the seed table to look at in this window
             bool multi = false;
             const uint4 *rg = nullptr;
             const uint4 *gq = nullptr;  // DOCRING: the current run's 8-byte postings in HBM (single-term test only)
@@ -1049,7 +1067,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                 }
                 // wlim == ~0: no single-term posting of the run can pass → the loop variant without that test; the first
                 // non-empty run has nothing to test against, the last one nobody to mark for
-                myvariant = (wlim != 0xFFFFFFFFu ? 4 : 0) | (multi && lane != __ffs(todo) - 1 ? 2 : 0) |
+                myvariant = (!C::SEEDED && wlim != 0xFFFFFFFFu ? 4 : 0) | (multi && lane != __ffs(todo) - 1 ? 2 : 0) |
                             (multi && lane != 31 - __clz(todo) ? 1 : 0);
             } else {
                 float *acc = (float *)map;
@@ -1210,15 +1228,24 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                             tdk = f.tie_dk;  // snapshot with tw: a stale (looser) pair stays valid, thresholds only tighten
                             pb = ra & ~((uint32_t)C::E - 1u);
                         }
-                        switch (variant) {
-                            case 0: pb = ree; break;  // nothing to learn from this run in this window
-                            case 3: run(std::true_type(), std::true_type(), std::false_type()); break;
-                            case 1: run(std::false_type(), std::true_type(), std::false_type()); break;
-                            case 2: run(std::true_type(), std::false_type(), std::false_type()); break;
-                            case 4: run(std::false_type(), std::false_type(), std::true_type()); break;
-                            case 5: run(std::false_type(), std::true_type(), std::true_type()); break;
-                            case 6: run(std::true_type(), std::false_type(), std::true_type()); break;
-                            default: run(std::true_type(), std::true_type(), std::true_type()); break;
+                        if constexpr (C::SEEDED) {  // no loop variant with the single-term test
+                            switch (variant & 3) {
+                                case 0: pb = ree; break;  // nothing to learn from this run in this window
+                                case 3: run(std::true_type(), std::true_type(), std::false_type()); break;
+                                case 1: run(std::false_type(), std::true_type(), std::false_type()); break;
+                                default: run(std::true_type(), std::false_type(), std::false_type()); break;
+                            }
+                        } else {
+                            switch (variant) {
+                                case 0: pb = ree; break;  // nothing to learn from this run in this window
+                                case 3: run(std::true_type(), std::true_type(), std::false_type()); break;
+                                case 1: run(std::false_type(), std::true_type(), std::false_type()); break;
+                                case 2: run(std::true_type(), std::false_type(), std::false_type()); break;
+                                case 4: run(std::false_type(), std::false_type(), std::true_type()); break;
+                                case 5: run(std::false_type(), std::true_type(), std::true_type()); break;
+                                case 6: run(std::true_type(), std::false_type(), std::true_type()); break;
+                                default: run(std::true_type(), std::true_type(), std::true_type()); break;
+                            }
                         }
                         if (nc > 64u) break;
                     }
