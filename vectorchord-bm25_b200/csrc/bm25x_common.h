@@ -88,8 +88,11 @@ struct bm25x_index {
     std::vector<uint32_t> h_df;        // host copy for query canonicalisation
     std::vector<uint8_t> h_keys;       // [n_terms*16] sorted keys (optional)
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // bm25x_search_batch: result downloads of one slice while the next one runs (lazy)
+    uint32_t slice_min = 32768;          // bm25x_search_batch cuts batches of >= 2 x this many queries into slices (0: never)
     std::vector<void *> allocs;
     int prune = 1;                     // MaxScore-style pruning in the search kernels
+    uint32_t seed_dense_div = 64;      // seeded launches hand queries with a list of n_docs / 64 postings or more to the plain kernel
     uint32_t seed_prune_min = 32768;   // seeded launches hand queries with a list this long (and 8x their shortest) to the pruning kernel
     int seed_max_terms = BM25X_SEED_MAX_TERMS;  // widest term-count class that runs seeded (4 or 8)
     int seed = 1;                      // 2..4-term classes, k <= BM25X_CHAMP_L, no prefilter: pools seeded from the champion lists

@@ -37,6 +37,7 @@ struct SearchParams {
     // champion lists (DeviceIndex::champ): seeded launches (RCfg::SEEDED) take their single-term documents from these
     const Posting *champ;
     const uint64_t *champ_off;
+    uint32_t seed_dense_div;            // seeded launch: a query with a list of n_docs / this postings or more goes to the plain kernel (0: never)
     uint32_t seed_prune_min;            // seeded launch: a query with a list this long, 8x its shortest one, goes to the pruning kernel
     unsigned long long *fetched;        // Σ postings actually loaded into shared memory (pruning statistics)
     uint8_t *pool_scratch;              // k > 1024: per-warp candidate pools in HBM (k_search_ring, RCfg::POOL_GLOBAL)

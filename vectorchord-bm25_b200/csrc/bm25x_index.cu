@@ -428,6 +428,12 @@ static int check_keys(const char *who, const uint8_t *term_key, uint32_t T) {
 static void apply_env_options(bm25x_index *ix) {
     if (const char *e = getenv("BM25X_SEED")) ix->seed = atoi(e) != 0;
     if (const char *e = getenv("BM25X_TWOPHASE")) ix->twophase = atoi(e) != 0;
+    if (const char *e = getenv("BM25X_SEED_FORCE")) {  // every eligible query through the seeded kernel, dense or skewed
+        if (atoi(e) != 0) {
+            ix->seed_prune_min = 0xFFFFFFFFu;
+            ix->seed_dense_div = 0u;
+        }
+    }
 }
 
 static int index_begin(const BuildMeta &m, int device, bm25x_index **ixp) {
@@ -935,6 +941,7 @@ extern "C" void bm25x_index_destroy(bm25x_index *ix) {
     for (void *p : ix->allocs) cudaFree(p);
     if (ix->h_stage) cudaFreeHost(ix->h_stage);
     if (ix->h_stage_free) cudaEventDestroy(ix->h_stage_free);
+    if (ix->copy_stream) cudaStreamDestroy(ix->copy_stream);
     if (ix->stream) cudaStreamDestroy(ix->stream);
     delete ix;
 }
@@ -1097,6 +1104,14 @@ extern "C" int bm25x_index_set_option(bm25x_index *ix, const char *name, int64_t
     }
     if (strcmp(name, "seed_prune_min") == 0) {  // seeded launches: list length from which a skewed query goes to the pruning kernel
         ix->seed_prune_min = value < 0 ? 0u : (value > 0xFFFFFFFFll ? 0xFFFFFFFFu : (uint32_t)value);
+        return BM25X_OK;
+    }
+    if (strcmp(name, "slice_min") == 0) {  // bm25x_search_batch: queries per slice of a pipelined call (0: one piece)
+        ix->slice_min = value < 0 ? 0u : (value > 0xFFFFFFFFll ? 0xFFFFFFFFu : (uint32_t)value);
+        return BM25X_OK;
+    }
+    if (strcmp(name, "seed_dense_div") == 0) {  // seeded launches: lists of n_docs / this or more go to the plain kernel (0: never)
+        ix->seed_dense_div = value < 0 ? 0u : (value > 0xFFFFFFFFll ? 0xFFFFFFFFu : (uint32_t)value);
         return BM25X_OK;
     }
     if (strcmp(name, "seed_max_terms") == 0) {  // widest term-count class that runs seeded: 4 or 8

@@ -175,7 +175,9 @@ extern "C" int bm25x_batch_prepare(bm25x_index *ix, uint32_t nq, const uint32_t 
     const uint32_t T = ix->d.n_terms;
     const uint32_t *h_df = ix->h_df.data();
     // ---- pass 1 (parallel): canonical terms of query i written in place of its raw terms (never longer) ----
-    const size_t n_raw = nq ? q_off[nq] : 0;
+    // (q_off may be a slice of a longer offset array: offsets are absolute into q_terms, the scratch is relative to base0)
+    const size_t base0 = nq ? q_off[0] : 0;
+    const size_t n_raw = nq && q_off[nq] >= base0 ? q_off[nq] - base0 : 0;
     std::vector<uint32_t> canon(n_raw ? n_raw : 1);
     std::vector<uint32_t> live(nq ? nq : 1);  // live terms of query i
     std::vector<uint64_t> cost(nq ? nq : 1);  // Σ df of query i
@@ -183,13 +185,13 @@ extern "C" int bm25x_batch_prepare(bm25x_index *ix, uint32_t nq, const uint32_t 
     const int nthr = nq < 4096 ? 1 : bm25x_host_threads(16);  // small batches: a parallel region costs more than the loop
 #pragma omp parallel for schedule(static, 1024) num_threads(nthr)
     for (uint32_t i = 0; i < nq; ++i) {
-        if (q_off[i + 1] < q_off[i]) {
+        if (q_off[i + 1] < q_off[i] || q_off[i] < base0 || q_off[i + 1] - base0 > n_raw) {
 #pragma omp critical
             { bad_query = (int)i; bad_kind = 1; }
             live[i] = 0;
             continue;
         }
-        uint32_t *dst = canon.data() + q_off[i];
+        uint32_t *dst = canon.data() + (q_off[i] - base0);
         const uint32_t n = q_off[i + 1] - q_off[i];
         uint32_t m = 0;
         for (uint32_t j = 0; j < n; ++j) {
@@ -337,7 +339,7 @@ extern "C" int bm25x_batch_prepare(bm25x_index *ix, uint32_t nq, const uint32_t 
         const int c = cls_of[m];
         hs[base_ids[c] + slot[i]] = i;
         hs[base_off[c] + slot[i] + 1] = tpos[i] + m;
-        const uint32_t *src = canon.data() + q_off[i];
+        const uint32_t *src = canon.data() + (q_off[i] - base0);
         uint32_t *dst = hs + base_terms[c] + tpos[i];
         for (uint32_t j = 0; j < m; ++j) {
             dst[j] = src[j];
@@ -424,6 +426,7 @@ extern "C" int bm25x_batch_run(bm25x_batch *b, void *stream_v, bm25x_search_stat
         sp.champ = d.champ;
         sp.champ_off = d.champ_off;
         sp.seed_prune_min = ix->seed_prune_min;
+        sp.seed_dense_div = ix->seed_dense_div;
         sp.post_off = d.post_off;
         sp.df = d.df;
         sp.blk_off = d.blk_off;
@@ -528,11 +531,105 @@ extern "C" int bm25x_batch_device_results(bm25x_batch *b, void **doc, void **sco
     return BM25X_OK;
 }
 
+// Large batches run as a pipeline of slices: while slice s is on the GPU the host canonicalises and uploads slice s + 1,
+// and the results of slice s - 1 travel to the host on a second stream.  Same results, row for row.
+static int search_batch_sliced(bm25x_index *ix, uint32_t nq, const uint32_t *q_off, const uint32_t *q_terms, uint32_t k,
+                               const uint8_t *allow, uint32_t *out_doc, float *out_score, double *out_score64,
+                               uint16_t *out_payload, uint32_t *out_n, bm25x_search_stats *stats, uint32_t n_slices) {
+    using clk = std::chrono::steady_clock;
+    BM25X_CUDA_TRY(cudaSetDevice(ix->device));
+    if (!ix->copy_stream) BM25X_CUDA_TRY(cudaStreamCreateWithFlags(&ix->copy_stream, cudaStreamNonBlocking));
+    std::vector<bm25x_batch *> bs(n_slices, nullptr);
+    std::vector<cudaEvent_t> done(n_slices, nullptr);
+    int rc = BM25X_OK;
+    double host_ms = 0.0;
+    auto fail = [&](int code) {
+        cudaStreamSynchronize(ix->stream);
+        cudaStreamSynchronize(ix->copy_stream);
+        for (uint32_t s = 0; s < n_slices; ++s) {
+            if (done[s]) cudaEventDestroy(done[s]);
+            if (bs[s]) bm25x_batch_destroy(bs[s]);
+        }
+        return code;
+    };
+    for (uint32_t s = 0; s < n_slices && rc == BM25X_OK; ++s) {
+        const uint32_t a = (uint32_t)(((uint64_t)nq * s) / n_slices), e = (uint32_t)(((uint64_t)nq * (s + 1)) / n_slices);
+        const auto t0 = clk::now();
+        // (q_off + a holds absolute offsets into q_terms: the slice is prepared in place)
+        rc = bm25x_batch_prepare(ix, e - a, q_off + a, q_terms, k, allow, &bs[s]);
+        host_ms += std::chrono::duration<double, std::milli>(clk::now() - t0).count();
+        if (rc != BM25X_OK) break;
+        bm25x_batch *b = bs[s];
+        cudaError_t ce = cudaSuccess;
+        if (stats) {
+            ce = cudaMemsetAsync(b->d_fetched, 0, sizeof(unsigned long long), ix->stream);
+            if (ce == cudaSuccess) ce = cudaEventRecord(b->ev0, ix->stream);
+        }
+        if (ce == cudaSuccess) {
+            rc = bm25x_batch_run(b, nullptr, nullptr);
+            if (rc != BM25X_OK) break;
+        }
+        if (ce == cudaSuccess && stats) ce = cudaEventRecord(b->ev1, ix->stream);
+        if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&done[s], cudaEventDisableTiming);
+        if (ce == cudaSuccess) ce = cudaEventRecord(done[s], ix->stream);
+        if (ce == cudaSuccess) ce = cudaStreamWaitEvent(ix->copy_stream, done[s], 0);
+        const size_t slots = (size_t)(e - a) * k, o = (size_t)a * k;
+        cudaStream_t cs = ix->copy_stream;
+        if (ce == cudaSuccess && out_doc) ce = cudaMemcpyAsync(out_doc + o, b->d_out_doc, 4 * slots, cudaMemcpyDeviceToHost, cs);
+        if (ce == cudaSuccess && out_score) ce = cudaMemcpyAsync(out_score + o, b->d_out_score, 4 * slots, cudaMemcpyDeviceToHost, cs);
+        if (ce == cudaSuccess && out_score64) ce = cudaMemcpyAsync(out_score64 + o, b->d_out_score64, 8 * slots, cudaMemcpyDeviceToHost, cs);
+        if (ce == cudaSuccess && out_payload) ce = cudaMemcpyAsync(out_payload + 3 * o, b->d_out_payload, 6 * slots, cudaMemcpyDeviceToHost, cs);
+        if (ce == cudaSuccess && out_n) ce = cudaMemcpyAsync(out_n + a, b->d_out_n, 4 * (size_t)(e - a), cudaMemcpyDeviceToHost, cs);
+        if (ce != cudaSuccess) {
+            bm25x_set_error("bm25x_search_batch (slice %u): %s", s, cudaGetErrorString(ce));
+            return fail(BM25X_ERR_CUDA);
+        }
+    }
+    if (rc != BM25X_OK) return fail(rc);
+    const auto t2 = clk::now();
+    cudaError_t ce = cudaStreamSynchronize(ix->copy_stream);  // every download (hence every kernel) has finished
+    if (ce != cudaSuccess) {
+        bm25x_set_error("bm25x_search_batch: %s", cudaGetErrorString(ce));
+        return fail(BM25X_ERR_CUDA);
+    }
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        for (uint32_t s = 0; s < n_slices; ++s) {
+            bm25x_batch *b = bs[s];
+            float ms = 0.f;
+            unsigned long long fetched = 0;
+            cudaEventElapsedTime(&ms, b->ev0, b->ev1);
+            cudaMemcpy(&fetched, b->d_fetched, sizeof(fetched), cudaMemcpyDeviceToHost);
+            uint32_t launches = 0;
+            for (int c = 0; c < kNumClasses; ++c)
+                if (b->groups[c].nq) launches += b->groups[c].d_q2 ? 2u : 1u;
+            stats->kernel_ms += ms;
+            stats->postings += b->postings;
+            stats->bytes_algo += 8ull * b->postings + 8ull * (uint64_t)b->live * b->k + 16ull * b->qterms;
+            stats->launches += launches;
+            stats->queries += b->live;
+            stats->postings_fetched += fetched;
+        }
+        stats->h2d_ms = host_ms;  // canonicalise + upload of all slices (overlapped with the kernels but for the first)
+        stats->d2h_ms = std::chrono::duration<double, std::milli>(clk::now() - t2).count();  // wait for the last download
+    }
+    for (uint32_t s = 0; s < n_slices; ++s) {
+        cudaEventDestroy(done[s]);
+        bm25x_batch_destroy(bs[s]);
+    }
+    return BM25X_OK;
+}
+
 extern "C" int bm25x_search_batch(bm25x_index *ix, uint32_t nq, const uint32_t *q_off, const uint32_t *q_terms,
                                   uint32_t k, const uint8_t *allow, uint32_t *out_doc, float *out_score,
                                   double *out_score64, uint16_t *out_payload, uint32_t *out_n,
                                   bm25x_search_stats *stats) {
     using clk = std::chrono::steady_clock;
+    if (ix && ix->slice_min && nq >= 2ull * ix->slice_min && q_off && k != 0) {
+        const uint32_t n_slices = std::min<uint32_t>(16u, nq / ix->slice_min);
+        return search_batch_sliced(ix, nq, q_off, q_terms, k, allow, out_doc, out_score, out_score64, out_payload, out_n,
+                                   stats, n_slices);
+    }
     bm25x_batch *b = nullptr;
     const auto t0 = clk::now();
     int rc = bm25x_batch_prepare(ix, nq, q_off, q_terms, k, allow, &b);

@@ -88,6 +88,9 @@ namespace {
 #ifndef BM25X_DOCRING_LOG_S
 #define BM25X_DOCRING_LOG_S 11  // log2 of the presence map bytes of a DOCRING class
 #endif
+#ifndef BM25X_RING_K2_SHIFT
+#define BM25X_RING_K2_SHIFT 0  // the second bit of a cell word comes from hash bits [SHIFT, SHIFT + 5)
+#endif
 #ifndef BM25X_RING_K2
 #define BM25X_RING_K2 1  // bit map only: TWO bits per document inside one 32-bit cell word (blocked Bloom filter, one
                          // shared-memory atomicOr / one load as before): false alarms ~ (fill)^2 instead of fill
@@ -311,13 +314,15 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
         // span the passes.
         const bool mp = C::M == 32 && m_total > 32u;
         if constexpr (C::SEEDED) {
-            // MaxScore pruning pays when one list is much longer than another (head term next to rare ones): such a
-            // query goes back to the plain kernel, which prunes
+            // The seeded kernel is the kernel of SPARSE lists.  A query goes back to the plain kernel (8-byte postings: dense
+            // windows sum tf / fieldnorm words straight from the rings; MaxScore pruning) when one of its lists is dense
+            // (>= n_docs / seed_dense_div postings: its windows overlap the other runs') or much longer than another one
+            // (head term next to rare ones: pruning pays).
             uint32_t dfl = 0u;
             if (lane < (int)m_total) dfl = p.df[p.q_terms[t0q + lane]];
             const uint32_t mx = __reduce_max_sync(FULL, dfl);
             const uint32_t mn = __reduce_min_sync(FULL, lane < (int)m_total ? dfl : 0xFFFFFFFFu);
-            if (p.prune && mx >= p.seed_prune_min && mx / 8u >= mn) {
+            if ((p.prune && mx >= p.seed_prune_min && mx / 8u >= mn) || (p.seed_dense_div && mx >= p.n_docs / p.seed_dense_div + 1u)) {
                 if (lane == 0) {
                     const uint32_t at = atomicAdd(&p.q2[0], 1u);
                     p.q2[2u + at] = (uint32_t)qi;
@@ -1142,7 +1147,8 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                                     const uint32_t slot = __umulhi(hsh, C::MAP_BYTES * 8u);
                                     uint32_t *cell = (uint32_t *)map + (slot >> 5);
 #if BM25X_RING_K2
-                                    const uint32_t msk = (1u << (slot & 31u)) | (1u << ((hsh >> 7) & 31u));
+                                    // second bit: low 5 bits of the hash (the shift wraps: no mask, no pre-shift)
+                                    const uint32_t msk = (1u << (slot & 31u)) | __funnelshift_l(0u, 1u, BM25X_RING_K2_SHIFT ? hsh >> BM25X_RING_K2_SHIFT : hsh);
                                     if (TEST) c = (*cell & msk) == msk;
                                     if (MARK && valid) atomicOr(cell, msk);
 #else
@@ -1193,7 +1199,11 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
 #endif
 #pragma unroll 1
                     while (ss < (uint32_t)C::M * slices && nc <= 64u) {
-                        const uint32_t jj = ss / slices, r = (ss % slices) * 32u + (uint32_t)lane;
+                        uint32_t jj = ss, r = (uint32_t)lane;
+                        if constexpr (C::SST > 32u) {
+                            jj = ss / slices;
+                            r += (ss % slices) * 32u;
+                        }
                         ++ss;
                         if (jj >= m || ((ne_mask >> jj) & 1u)) continue;  // a pruned term's documents cannot enter
                         const uint32_t d = seeds[jj * C::SST + r].doc;
