@@ -220,6 +220,14 @@ __device__ __forceinline__ uint32_t ring_find(const typename C::RT *rg, uint32_t
     return 0u;
 }
 
+// posting index of `doc` in [a, e), INF when absent (doc-id-only rings: the posting word is fetched by the caller, so that
+// the loads of all holders of a candidate are in flight together)
+template <class C, int TOP = C::LOG_RMAX>
+__device__ __forceinline__ uint32_t ring_find_pos(const typename C::RT *rg, uint32_t mask, uint32_t a, uint32_t e, uint32_t doc) {
+    const uint32_t l = ring_lower_bound<C, TOP>(rg, mask, a, e, doc);
+    return (l < e && ring_doc(rg, l & mask) == doc) ? l : INF;
+}
+
 // ---- probes of a term that is not streamed any more (candidates only; replaces Cursor::seek_block / seek of the
 // reference's parked cursors, search.rs:412-466): block table first (SummaryTuple.{min,max}_document_id), then inside
 // the 128-posting block.  `steps` counts the table entries / postings read (pruning statistics).
@@ -828,36 +836,49 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_search_ring(const __grid_cons
                         return wi;
                     };
                     if constexpr (C::DOCRING) {
-                        // searches first (doc ids in the rings), posting words of the holders from HBM afterwards
-                        bool found = false;
+                        // searches first (doc ids in the rings: posting indices of the holders), then the posting words of ALL
+                        // holders from HBM with the loads in flight together (one DRAM latency per pass, not one per holder).
+                        // A lone posting of a run that cannot pass alone is dropped unread; so is a seed another run holds.
                         if (C::M == 3 && pairs) {
                             const uint32_t o = (lane & 1) ? (j == 2u ? 1u : 2u) : (j == 0u ? 1u : 0u);
                             const uint32_t ao = __shfl_sync(FULL, rd, o), eo = __shfl_sync(FULL, e, o);
                             const uint64_t pbo = __shfl_sync(FULL, pbase, o);
+                            uint32_t l = INF;
+                            if (has) l = ring_find_pos<C, C::LOG_R>(rings + o * C::R, C::R - 1u, ao, eo, doc);
+                            const bool hit = l != INF;
+                            const uint32_t hitx = __shfl_xor_sync(FULL, hit ? 1u : 0u, 1);  // (every lane takes part: no short circuit)
+                            const bool anyhit = hit || hitx != 0u;
+                            const bool live = has && (is_seed ? !anyhit : (anyhit || solo_j));  // (same in both lanes of a pair)
                             uint32_t wo = 0u;
-                            if (has) wo = ring_find<C, C::LOG_R>(rings + o * C::R, C::R - 1u, ao, eo, doc, p.post + pbo);
+                            if (live && hit) wo = __ldg(&(p.post + pbo)[l].w);
+                            if (live && !(lane & 1) && !is_seed) own.w = __ldg(&gown->w);
                             const uint32_t wx = __shfl_xor_sync(FULL, wo, 1);  // the partner's run
                             const uint32_t ox = (lane & 1) ? (j == 0u ? 1u : 0u) : (j == 2u ? 1u : 2u);
-                            has = has && !(lane & 1);
+                            has = live && !(lane & 1);
 #pragma unroll
                             for (int i = 0; i < C::M; ++i) wv[i] = (uint32_t)i == o ? wo : ((uint32_t)i == ox ? wx : 0u);
-                            found = (wo | wx) != 0u;
                         } else {
+                            uint32_t lv[C::M];
+                            bool anyhit = false;
 #pragma unroll
                             for (int i = 0; i < C::M; ++i) {
                                 const uint32_t ai = __shfl_sync(FULL, rd, i), ei = __shfl_sync(FULL, e, i);
-                                const uint64_t pbi = __shfl_sync(FULL, pbase, i);
                                 const uint32_t ib = ring_base(i), im = ring_mask(i);
+                                lv[i] = INF;
                                 if (i < (int)m && has && (uint32_t)i != j && !((ne_mask >> i) & 1u)) {
-                                    wv[i] = small_rings ? ring_find<C, C::LOG_R>(rings + ib, im, ai, ei, doc, p.post + pbi)
-                                                        : ring_find<C>(rings + ib, im, ai, ei, doc, p.post + pbi);
-                                    found = found || wv[i] != 0u;
+                                    lv[i] = small_rings ? ring_find_pos<C, C::LOG_R>(rings + ib, im, ai, ei, doc)
+                                                        : ring_find_pos<C>(rings + ib, im, ai, ei, doc);
+                                    anyhit = anyhit || lv[i] != INF;
                                 }
                             }
-                        }
-                        if (!by_doc && !is_seed) {
-                            has = has && (found || solo_j);  // a lone posting of a run that cannot pass alone: dropped unread
-                            if (has) own.w = __ldg(&gown->w);
+                            const bool live = has && (is_seed ? !anyhit : (by_doc || anyhit || solo_j));
+#pragma unroll
+                            for (int i = 0; i < C::M; ++i) {
+                                const uint64_t pbi = __shfl_sync(FULL, pbase, i);
+                                if (live && lv[i] != INF) wv[i] = __ldg(&(p.post + pbi)[lv[i]].w);
+                            }
+                            if (live && !by_doc && !is_seed) own.w = __ldg(&gown->w);
+                            has = live;
                         }
 #pragma unroll
                         for (int i = 0; i < C::M; ++i) {
