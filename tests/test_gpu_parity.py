@@ -163,6 +163,44 @@ def test_kernel_paths_identical(m, orc, zipf):
     ix.close()
 
 
+def test_replica_same_device_identical(m, orc):
+    """bm25x_index_get_layout / alloc_replica / finalize_replica on ONE GPU: the 13 replicated arrays copied device to
+    device (what shard.replicate_index does with NCCL broadcasts), the derived structures (doc-id copy, champion lists)
+    rebuilt by finalize_replica — the replica answers like the original, seeded and plain kernel."""
+    import ctypes
+    rt = None
+    for name in ("libcudart.so", "libcudart.so.12", "/usr/local/cuda/lib64/libcudart.so"):
+        try:
+            rt = ctypes.CDLL(name)
+            break
+        except OSError:
+            pass
+    assert rt is not None, "libcudart not found"
+    rt.cudaMemcpy.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]
+    c = m.synth_corpus(95, 60000, 5000, 8, 48, 0.0)
+    q_off, q_terms = m.synth_queries(96, 150, c.n_terms, 1, 8, c.post_off, 0.0)
+    ix = m.Index.from_corpus(c)
+    lay = ix.layout()
+    rep = m.Index.alloc_replica(lay, 0)
+    with pytest.raises(m.Bm25xError):  # not finalized yet
+        rep.search_batch(q_off, q_terms, 10)
+    rl = rep.layout()
+    for i in range(len(lay.dev_ptr)):
+        assert rl.bytes[i] == lay.bytes[i]
+        assert rt.cudaMemcpy(rl.dev_ptr[i], lay.dev_ptr[i], lay.bytes[i], 3) == 0  # cudaMemcpyDeviceToDevice
+    rep.finalize_replica()
+    for seed in (1, 0):
+        ix.set_option("seed", seed)
+        rep.set_option("seed", seed)
+        for k in (10, 100):
+            a, b = ix.search_batch(q_off, q_terms, k), rep.search_batch(q_off, q_terms, k)
+            for key in ("doc", "score", "score64", "n"):
+                assert np.array_equal(a[key], b[key]), (key, seed, k)
+    _compare(b, _oracle_index(orc, c), q_off[:30], q_terms, 100, what="replica")
+    rep.close()
+    ix.close()
+
+
 def test_sliced_search_batch_identical(m, orc):
     """bm25x_search_batch pipelines large batches as slices (prepare of slice s + 1 and download of slice s - 1 overlap the
     kernels of slice s): same rows as one piece, with and without a prefilter bitmap; statistics add up."""
