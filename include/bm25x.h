@@ -135,8 +135,15 @@ int bm25x_index_finalize_replica(bm25x_index *idx);
  * bounds (the token-level WAND bound of the reference: TokenTuple.wand_fieldnorm/wand_term_frequency,
  * flush.rs:101-120, search.rs:363) stay below 5 % of the current k-th score are no longer streamed; their postings
  * are looked up in HBM only for the candidates.  Results are identical with it on or off.
- * "twophase" (default 1): queries of 2..4 terms with limit <= 224 run as two launches — 8-byte postings while single
- * postings can still enter the top-k, then doc ids only (half the bytes) for the rest.  Results identical on or off. */
+ * "seed" (default 1): queries of 2..8 terms with limit <= 128 and no prefilter bitmap run through the SEEDED kernel —
+ * the documents that hold a single query term come from per-term champion lists (the term's best 128 postings in
+ * result order, built with the index), so the stream reads doc ids only (half the bytes) and never tests a posting on
+ * its own; "seed_max_terms" (4 | 8), "seed_dense_div" (default 64: queries with a list of >= n_docs / 64 postings go
+ * back to the plain kernel; 0: never), "seed_prune_min" (default 32768: so do queries with a list this long and 8x
+ * their shortest one — pruning pays).  "twophase" (default 0): queries of 2..4 terms with limit <= 224 that the seeded
+ * kernel does not take run as two launches — 8-byte postings while single postings can still enter the top-k, then
+ * doc ids only.  "slice_min" (default 32768): bm25x_search_batch pipelines batches of >= 2 x this many queries as slices
+ * (upload / kernels / download overlap; 0: one piece).  None of these changes a result bit. */
 int bm25x_index_set_option(bm25x_index *idx, const char *name, int64_t value);
 /* df of every term (TokenTuple.number_of_documents), host copy. */
 int bm25x_index_get_df(const bm25x_index *idx, uint32_t *df_out);

@@ -370,8 +370,8 @@ extern "C" int bm25x_batch_prepare(bm25x_index *ix, uint32_t nq, const uint32_t 
     for (int c = 0; c < kNumClasses; ++c) {
         Group &g = b->groups[c];
         if (g.nq && (two_phase_class(ix, g.M, k) || seeded_class(ix, g.M, k, allow))) {
-            BTRY(batch_alloc(b, &g.d_q2, (size_t)g.nq + 2));
-            BTRY(batch_alloc(b, &g.d_resume, (size_t)g.nq));
+            BTRY(batch_alloc(b, &g.d_q2, (size_t)g.nq + 2));  // hand-over list of the class (suspended / handed-back queries)
+            if (two_phase_class(ix, g.M, k)) BTRY(batch_alloc(b, &g.d_resume, (size_t)g.nq));
         }
     }
     size_t slots = (size_t)nq * k;
@@ -466,7 +466,7 @@ extern "C" int bm25x_batch_run(bm25x_batch *b, void *stream_v, bm25x_search_stat
             if (rc != BM25X_OK) return rc;
             launches++;
             rc = launch_ring_k(ix, sp, g.M, 4, st);
-        } else if (g.d_q2 && ix->twophase) {
+        } else if (g.d_q2 && g.d_resume && ix->twophase) {
             // first phase: 8-byte postings until no posting can enter the top-k alone; second phase: the suspended
             // queries go on with doc ids only (bm25x_search_ring.cuh, RCfg::PH)
             BM25X_CUDA_TRY(cudaMemsetAsync(g.d_q2, 0, 2 * sizeof(uint32_t), st));
