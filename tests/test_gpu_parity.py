@@ -201,6 +201,43 @@ def test_replica_same_device_identical(m, orc):
     ix.close()
 
 
+def test_broker_over_an_index_matches_direct_search(m, orc):
+    """The batching broker (include/bm25x_broker.h) over a real index handle: 16 concurrent callers, limits of several
+    classes — every caller gets exactly the rows of a direct search with its own limit."""
+    import threading
+    bm = __import__(m.__name__ + ".bm25x", fromlist=["x"])
+    c = m.synth_corpus(97, 30000, 2000, 6, 40, 0.5)
+    q_off, q_terms = m.synth_queries(98, 96, c.n_terms, 1, 6, c.post_off, 0.5)
+    ix = m.Index.from_corpus(c)
+    limits = [1, 10, 32, 40, 128, 300]
+    want = {k: ix.search_batch(q_off, q_terms, k, want_payload=True) for k in limits}
+    br = bm.Broker(index=ix, max_batch=64, max_wait_us=5000)
+    got, errs = [None] * 96, []
+
+    def client(t):
+        try:
+            for i in range(t, 96, 16):
+                got[i] = (limits[i % len(limits)], br.search(q_terms[q_off[i]:q_off[i + 1]], limits[i % len(limits)], want_payload=True))
+        except Exception as e:  # pragma: no cover
+            errs.append(e)
+
+    ts = [threading.Thread(target=client, args=(t,)) for t in range(16)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs, errs
+    for i, (k, (docs, s64, pay)) in enumerate(got):
+        n = int(want[k]["n"][i])
+        assert len(docs) == n
+        assert np.array_equal(docs, want[k]["doc"][i, :n]) and np.array_equal(s64, want[k]["score64"][i, :n])
+        assert np.array_equal(pay, want[k]["payload"][i, :n])
+    st = br.stats()
+    assert st.requests == 96 and st.batches < 96
+    br.close()
+    ix.close()
+
+
 def test_sliced_search_batch_identical(m, orc):
     """bm25x_search_batch pipelines large batches as slices (prepare of slice s + 1 and download of slice s - 1 overlap the
     kernels of slice s): same rows as one piece, with and without a prefilter bitmap; statistics add up."""

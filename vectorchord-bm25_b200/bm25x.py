@@ -63,6 +63,21 @@ class IndexLayout(C.Structure):
                 ("bytes", C.c_uint64 * N_ARRAYS), ("device", C.c_int)]
 
 
+class BrokerOptions(C.Structure):  # bm25x_broker_options (include/bm25x_broker.h)
+    _fields_ = [("max_batch", C.c_uint32), ("max_wait_us", C.c_uint32), ("ring_slots", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class BrokerStats(C.Structure):  # bm25x_broker_stats
+    _fields_ = [("requests", C.c_uint64), ("batches", C.c_uint64), ("max_batch_seen", C.c_uint64),
+                ("ring_full_waits", C.c_uint64), ("rejected", C.c_uint64)]
+
+
+# bm25x_broker_backend: (ctx, nq, q_off, q_terms, k, out_doc, out_score, out_score64, out_payload, out_n) -> status
+BROKER_BACKEND = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_uint32,
+                             C.POINTER(C.c_uint32), C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_uint16),
+                             C.POINTER(C.c_uint32))
+
+
 class SearchStats(C.Structure):
     _fields_ = [("kernel_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double), ("postings", C.c_uint64),
                 ("bytes_algo", C.c_uint64), ("launches", C.c_uint32), ("queries", C.c_uint32),
@@ -131,6 +146,12 @@ def load_library():
                                       u32p, u32p]
     L.bm25x_intern.argtypes = [u8p, u8p, C.c_size_t, u8p]
     L.bm25x_blake3_keyed16.argtypes = [u8p, u8p, C.c_size_t, u8p]
+    L.bm25x_broker_create.argtypes = [vp, C.POINTER(BrokerOptions), C.POINTER(vp)]
+    L.bm25x_broker_create_with_backend.argtypes = [BROKER_BACKEND, vp, C.POINTER(BrokerOptions), C.POINTER(vp)]
+    L.bm25x_broker_search.argtypes = [vp, u32p, C.c_uint32, C.c_uint32, u32p, f64p, u16p, u32p]
+    L.bm25x_broker_get_stats.argtypes = [vp, C.POINTER(BrokerStats)]
+    L.bm25x_broker_destroy.argtypes = [vp]
+    L.bm25x_broker_destroy.restype = None
     L.bm25x_last_error.restype = C.c_char_p
     L.bm25x_device_count.restype = C.c_int
     _lib = L
@@ -530,3 +551,40 @@ class Batch:
             self.close()
         except Exception:
             pass
+
+
+class Broker:
+    """Batching broker (include/bm25x_broker.h): concurrent single-query callers, one backend call per batch.
+    Broker(index) batches into bm25x_search_batch; Broker(backend=callable) into any function of the backend signature
+    (the callable receives raw ctypes pointers)."""
+
+    def __init__(self, index=None, backend=None, max_batch=0, max_wait_us=0, ring_slots=0):
+        L = load_library()
+        opt = BrokerOptions(max_batch, max_wait_us, ring_slots, 0)
+        self.h = C.c_void_p()
+        self._keep = None
+        if backend is not None:
+            self._keep = BROKER_BACKEND(backend)
+            _check(L.bm25x_broker_create_with_backend(self._keep, None, C.byref(opt), C.byref(self.h)))
+        else:
+            self._keep = index
+            _check(L.bm25x_broker_create(index.h, C.byref(opt), C.byref(self.h)))
+
+    def search(self, terms, k, want_payload=False):
+        terms = np.ascontiguousarray(terms, dtype=np.uint32)
+        kk = max(int(k), 1)
+        doc, s64, n = np.empty(kk, np.uint32), np.empty(kk, np.float64), C.c_uint32(0)
+        pay = np.empty((kk, 3), np.uint16) if want_payload else None
+        _check(load_library().bm25x_broker_search(self.h, _p(terms, C.c_uint32), len(terms), int(k), _p(doc, C.c_uint32),
+                                                  _p(s64, C.c_double), _p(pay, C.c_uint16), C.byref(n)))
+        return (doc[:n.value], s64[:n.value]) + ((pay[:n.value],) if want_payload else ())
+
+    def stats(self) -> BrokerStats:
+        st = BrokerStats()
+        _check(load_library().bm25x_broker_get_stats(self.h, C.byref(st)))
+        return st
+
+    def close(self):
+        if self.h:
+            load_library().bm25x_broker_destroy(self.h)
+            self.h = C.c_void_p()

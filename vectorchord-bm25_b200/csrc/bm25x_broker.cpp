@@ -52,8 +52,9 @@ struct bm25x_broker {
     std::vector<Request *> ring;
     size_t head = 0, count = 0;
     mutable std::mutex mu;
-    std::condition_variable cv_work, cv_space, cv_done;
+    std::condition_variable cv_work, cv_space, cv_done, cv_idle;
     bool stop = false;
+    uint32_t inflight = 0;  // callers inside bm25x_broker_search (destroy waits for them to leave)
     bm25x_broker_stats st{};
     std::thread worker;
 
@@ -203,16 +204,21 @@ extern "C" int bm25x_broker_search(bm25x_broker *b, const uint32_t *terms, uint3
         b->st.rejected++;
         return reject;
     }
+    b->inflight++;
+    auto leave = [&](int rc) {  // (still under the lock: destroy deletes the broker only after the last caller has left)
+        if (--b->inflight == 0) b->cv_idle.notify_all();
+        return rc;
+    };
     if (b->stop) {
         bm25x_set_error("bm25x_broker_search: the broker is shutting down");
-        return BM25X_ERR_INVALID;
+        return leave(BM25X_ERR_INVALID);
     }
     if (b->count == b->ring.size()) {
         b->st.ring_full_waits++;
         b->cv_space.wait(lk, [&] { return b->count < b->ring.size() || b->stop; });
         if (b->stop) {
             bm25x_set_error("bm25x_broker_search: the broker is shutting down");
-            return BM25X_ERR_INVALID;
+            return leave(BM25X_ERR_INVALID);
         }
     }
     b->ring[(b->head + b->count) % b->ring.size()] = &r;
@@ -220,7 +226,7 @@ extern "C" int bm25x_broker_search(bm25x_broker *b, const uint32_t *terms, uint3
     b->cv_work.notify_one();
     b->cv_done.wait(lk, [&] { return r.done; });
     if (r.rc != BM25X_OK) bm25x_set_error("bm25x_broker_search: the batch holding this query failed with status %d", r.rc);
-    return r.rc;
+    return leave(r.rc);
 }
 
 extern "C" int bm25x_broker_get_stats(const bm25x_broker *b, bm25x_broker_stats *out) {
@@ -242,5 +248,9 @@ extern "C" void bm25x_broker_destroy(bm25x_broker *b) {
     b->cv_work.notify_all();
     b->cv_space.notify_all();
     if (b->worker.joinable()) b->worker.join();
+    {   // callers that were being answered are still on their way out
+        std::unique_lock<std::mutex> lk(b->mu);
+        b->cv_idle.wait(lk, [&] { return b->inflight == 0; });
+    }
     delete b;
 }
