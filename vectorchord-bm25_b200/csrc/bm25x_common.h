@@ -103,4 +103,9 @@ struct bm25x_index {
     cudaEvent_t h_stage_free = nullptr;  // recorded after the upload that last read h_stage
     bool h_stage_busy = false;
     std::mutex stage_mutex;
+    // bm25x_evaluate_batch: tables that depend on the index alone, built on first use (idf per term with the host libm,
+    // fieldnorm -> length), kept on the device
+    double *eval_idf = nullptr;
+    uint32_t *eval_fn_len = nullptr;
+    std::mutex eval_mutex;
 };

@@ -758,14 +758,31 @@ extern "C" int bm25x_evaluate_batch(bm25x_index *ix, uint32_t n_pairs, const uin
     BM25X_CUDA_TRY(cudaSetDevice(ix->device));
     const uint32_t nd = d_off[n_pairs], nqt = q_off[n_pairs];
     const uint32_t T = ix->d.n_terms;
-    // idf table (bm25.rs:285-289) with the host libm, like the reference's f64::ln
-    std::vector<double> h_idf(T ? T : 1);
-    for (uint32_t t = 0; t < T; ++t)
-        h_idf[t] = log(((double)ix->d.n_docs + 1.0) / ((double)ix->h_df[t] + 0.5));
-    uint32_t h_fn[256];
-    for (int f = 0; f < 256; ++f) h_fn[f] = bm25x_fieldnorm_to_length((uint8_t)f);
-    uint32_t *g_doff = nullptr, *g_dt = nullptr, *g_df = nullptr, *g_qoff = nullptr, *g_qt = nullptr, *g_fn = nullptr;
-    double *g_idf = nullptr, *g_out = nullptr;
+    {   // idf table (bm25.rs:285-289) with the host libm, like the reference's f64::ln, and the fieldnorm -> length table:
+        // they depend on the index alone — built once, kept on the device (freed with the handle)
+        std::lock_guard<std::mutex> lk(ix->eval_mutex);
+        if (!ix->eval_idf) {
+            std::vector<double> h_idf(T ? T : 1);
+            for (uint32_t t = 0; t < T; ++t)
+                h_idf[t] = log(((double)ix->d.n_docs + 1.0) / ((double)ix->h_df[t] + 0.5));
+            uint32_t h_fn[256];
+            for (int f = 0; f < 256; ++f) h_fn[f] = bm25x_fieldnorm_to_length((uint8_t)f);
+            double *d_idf = nullptr;
+            uint32_t *d_fn = nullptr;
+            BM25X_CUDA_TRY(cudaMalloc((void **)&d_idf, 8 * (size_t)(T ? T : 1)));
+            ix->allocs.push_back((void *)d_idf);
+            BM25X_CUDA_TRY(cudaMalloc((void **)&d_fn, sizeof(h_fn)));
+            ix->allocs.push_back((void *)d_fn);
+            BM25X_CUDA_TRY(cudaMemcpy(d_idf, h_idf.data(), 8 * (size_t)(T ? T : 1), cudaMemcpyHostToDevice));
+            BM25X_CUDA_TRY(cudaMemcpy(d_fn, h_fn, sizeof(h_fn), cudaMemcpyHostToDevice));
+            ix->eval_fn_len = d_fn;
+            ix->eval_idf = d_idf;
+        }
+    }
+    uint32_t *g_doff = nullptr, *g_dt = nullptr, *g_df = nullptr, *g_qoff = nullptr, *g_qt = nullptr;
+    uint32_t *const g_fn = ix->eval_fn_len;
+    double *const g_idf = ix->eval_idf;
+    double *g_out = nullptr;
     int rc = BM25X_OK;
     cudaError_t e = cudaSuccess;
     auto A = [&](void **p, size_t bytes) {
@@ -776,8 +793,6 @@ extern "C" int bm25x_evaluate_batch(bm25x_index *ix, uint32_t n_pairs, const uin
     A((void **)&g_df, 4 * (size_t)nd);
     A((void **)&g_qoff, 4 * ((size_t)n_pairs + 1));
     A((void **)&g_qt, 4 * (size_t)nqt);
-    A((void **)&g_fn, 4 * 256);
-    A((void **)&g_idf, 8 * (size_t)(T ? T : 1));
     A((void **)&g_out, 8 * (size_t)n_pairs);
     auto H = [&](void *dst, const void *src, size_t bytes) {
         if (e == cudaSuccess && bytes) e = cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice);
@@ -787,8 +802,6 @@ extern "C" int bm25x_evaluate_batch(bm25x_index *ix, uint32_t n_pairs, const uin
     H(g_df, d_tfs, 4 * (size_t)nd);
     H(g_qoff, q_off, 4 * ((size_t)n_pairs + 1));
     H(g_qt, q_terms, 4 * (size_t)nqt);
-    H(g_fn, h_fn, sizeof(h_fn));
-    H(g_idf, h_idf.data(), 8 * (size_t)T);
     if (e == cudaSuccess) {
         k_evaluate<<<(n_pairs + 127) / 128, 128>>>(n_pairs, g_doff, g_dt, g_df, g_qoff, g_qt, g_fn, g_idf, ix->d.s1d,
                                                    ix->d.df, T, ix->k1, g_out);
@@ -804,8 +817,6 @@ extern "C" int bm25x_evaluate_batch(bm25x_index *ix, uint32_t n_pairs, const uin
     cudaFree(g_df);
     cudaFree(g_qoff);
     cudaFree(g_qt);
-    cudaFree(g_fn);
-    cudaFree(g_idf);
     cudaFree(g_out);
     return rc;
 }
