@@ -1,4 +1,4 @@
-// bm25x_search_ring.cuh — kernel v6 (sm_100a): one WARP per query, ring stages + presence map.
+// bm25x_search_ring.cuh — kernel v6 (sm_100a): one WARP per query, ring stages + presence map, seeded flavour.
 //
 // Replaces the per-query cursor walk of bm25::search (crates/bm25/src/search.rs:137-282) for a whole batch: every
 // warp of the persistent grid is a complete query engine (lane j owns term j of its query).
@@ -11,11 +11,11 @@
 //             one is processed.
 //   window    chunk = doc window [lo, hi): hi = the smallest "last landed doc" over the runs that still have postings
 //             in HBM; each lane binary-searches hi in its run → exact in-window range [rd, e), nothing scanned twice.
-//   union     runs are processed in ascending order; run j first TESTS each of its documents against a byte map that
-//             holds the marks of runs < j, then MARKS it (one multiplicative hash, plain st.shared.u8 of the chunk's
-//             generation tag: idempotent stores, no atomics, no clearing — stale tags of older chunks never match).
-//             A document held by two runs is therefore always detected by the later run's posting (no false
-//             negatives); false alarms (slot shared with another document) are a few per cent.
+//   union     runs are processed in ascending order; run j first TESTS each of its documents against a presence map
+//             that holds the marks of runs < j, then MARKS it.  The map is a blocked Bloom filter: a document sets /
+//             tests two bits of one 32-bit word (one multiplicative hash; one shared-memory load, one atomicOr), cleared
+//             per window.  A document held by two runs is therefore always detected by the later run's posting (no
+//             false negatives); false alarms (both bits set by other documents) are below one per cent.
 //   single    a document held by one run only can enter the top-k only if its term frequency passes the threshold:
 //             one integer compare per posting (w > wlim_j, wlim_j from the exact threshold solved for tf), plus the
 //             tie shortcut (same (run, tf, fieldnorm) signature as the k-th entry ⇒ identical score ⇒ rejected
@@ -28,6 +28,17 @@
 //   dense     windows in which the runs overlap heavily (head terms) are summed in a dense f32 accumulator indexed by
 //             doc - lo instead (the window is clamped to the accumulator size: a ring can be consumed partially).
 //   pruning   MaxScore-style, as v5 (token-level bounds; non-streamed terms are probed in HBM for candidates).
+//
+// Flavours (RCfg::PH).  The above is the PLAIN kernel (PH 0; PH 4 = the same, fed from a device-side query list).  The
+// SEEDED kernel (PH 3; 2..8 terms, k <= 128, no prefilter) takes the documents that hold a single query term from per-term
+// champion lists (DeviceIndex::champ: a term's best postings in result order — such a document can only be in the
+// top-k if it is among the first k champions of its term).  Its seeds join the candidate list of the doc window they
+// fall into and go through the ordinary verification; the stream itself then never tests a posting on its own, so the
+// rings hold doc ids only (DeviceIndex::pdoc, 4 B per posting: twice the postings per ring byte, half the HBM bytes),
+// posting words are fetched from HBM for the holders of verified documents alone, and there is no pruning: queries
+// with a dense list or a list much longer than another one are handed back to the plain kernel (PH 4 launch behind
+// it).  PH 1 / 2 (off by default): plain kernel that suspends a query once no posting can pass alone + doc-id-only kernel
+// that resumes it.
 //
 // Exactness: the f32 filter only rejects F < Sk·(1-2^-18) and exact-score ties by signature;
 // everything else is ranked by (f64 score desc, doc id asc).
