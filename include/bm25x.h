@@ -226,6 +226,11 @@ int bm25x_merge_topk(uint32_t nq, uint32_t k, const uint32_t *doc_a, const float
                      const double *score64_b, const uint16_t *payload_b, const uint32_t *n_b, uint32_t doc_base_b,
                      uint32_t *out_doc, float *out_score, double *out_score64, uint16_t *out_payload, uint32_t *out_n);
 
+/* Invariants of the reference's vector types (crates/bm25/src/vector.rs:46-134): n vectors in CSR form, keys strictly
+ * ascending inside a vector, term frequencies (tfs, NULL for Query-like vectors) non-zero — what Document::new / Query::new
+ * enforce with expect("invalid data").  BM25X_ERR_INVALID names the first offending vector.  Host only. */
+int bm25x_check_vectors(uint32_t n, const uint32_t *off, const uint32_t *terms, const uint32_t *tfs);
+
 /* ---- bm25::evaluate (crates/bm25/src/evaluate.rs:22-74) behind `<&>` without an index scan
  * (src/index/operators.rs:22-55): pair p scores document [d_off[p], d_off[p+1]) (sorted distinct term ordinals
  * with tfs) against query [q_off[p], q_off[p+1]) (sorted distinct ordinals).  out[p] = positive f64 score. */

@@ -126,3 +126,20 @@ def test_struct_layouts_match_the_header(m):
         assert C.sizeof(cls) == int(size), f"{name}: ctypes size {C.sizeof(cls)} != C {size}"
         assert [f for f, _ in cls._fields_] == fields, f"{name}: field order"
         assert [getattr(cls, f).offset for f in fields] == [int(o) for o in offs], f"{name}: field offsets"
+
+
+def test_vector_invariants_in_c(m):
+    """bm25x_check_vectors = what Document::new / Query::new enforce (crates/bm25/src/vector.rs:46-134): strictly ascending
+    keys, non-zero term frequencies — the C side of the boundary refuses what the reference's types cannot hold."""
+    m.check_vectors([0, 3, 3, 5], [1, 5, 9, 2, 7], [1, 2, 3, 1, 1])            # valid, incl. an empty vector
+    m.check_vectors([0, 2], [4, 8])                                              # Query-like: no tfs
+    for off, terms, tfs, what in [([0, 3], [1, 5, 5], [1, 1, 1], "strictly ascending"),      # duplicate key
+                                  ([0, 3], [1, 9, 5], [1, 1, 1], "strictly ascending"),      # unsorted
+                                  ([0, 2, 4], [1, 2, 3, 4], [1, 1, 0, 1], "zero term frequency"),
+                                  ([0, 3, 2], [1, 2, 3], [1, 1, 1], "offsets not monotone"),
+                                  ([0, 2], [7, 7], None, "strictly ascending")]:
+        with pytest.raises(m.Bm25xError) as e:
+            m.check_vectors(off, terms, tfs)
+        assert e.value.code == 1 and "invalid data" in str(e.value) and what in str(e.value)
+    # keys restart between vectors: each vector is checked on its own
+    m.check_vectors([0, 2, 4], [5, 9, 1, 2], [1, 1, 1, 1])

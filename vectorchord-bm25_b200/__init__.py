@@ -6,7 +6,8 @@ host-side interface for the path (`bm25::search` / `bm25::evaluate`, Document / 
 falls back to a CPU implementation: if the library or a B200 is missing, calls raise.
 """
 from .bm25x import (Bm25xError, Index, Batch, SearchStats, IndexLayout, synth_corpus, synth_queries, load_library, build_library,
-                    device_count, Document, Query, MAX_K, MAX_QUERY_TERMS, TERM_MISSING, merge_topk)
+                    device_count, Document, Query, MAX_K, MAX_QUERY_TERMS, TERM_MISSING, merge_topk, check_vectors, Broker)
 
 __all__ = ["Bm25xError", "Index", "Batch", "SearchStats", "IndexLayout", "synth_corpus", "synth_queries", "load_library",
-           "build_library", "device_count", "Document", "Query", "MAX_K", "MAX_QUERY_TERMS", "TERM_MISSING", "merge_topk"]
+           "build_library", "device_count", "Document", "Query", "MAX_K", "MAX_QUERY_TERMS", "TERM_MISSING", "merge_topk",
+           "check_vectors", "Broker"]

@@ -138,6 +138,7 @@ def load_library():
     L.bm25x_batch_destroy.argtypes = [vp]
     L.bm25x_batch_destroy.restype = None
     L.bm25x_evaluate_batch.argtypes = [vp, C.c_uint32, u32p, u32p, u32p, u32p, u32p, f64p]
+    L.bm25x_check_vectors.argtypes = [C.c_uint32, u32p, u32p, u32p]
     L.bm25x_synth_generate.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_double,
                                        C.c_int, C.POINTER(_Synth)]
     L.bm25x_synth_free.argtypes = [C.POINTER(_Synth)]
@@ -183,6 +184,15 @@ def _check(rc):
 
 def _p(a, ty):
     return a.ctypes.data_as(C.POINTER(ty)) if a is not None else None
+
+
+def check_vectors(off, terms, tfs=None):
+    """bm25x_check_vectors: the Document / Query invariants of crates/bm25/src/vector.rs:46-134 for n vectors in CSR form
+    (keys strictly ascending, tfs non-zero); raises Bm25xError(1, "invalid data: ...")."""
+    off = np.ascontiguousarray(off, dtype=np.uint32)
+    terms = np.ascontiguousarray(terms, dtype=np.uint32)
+    tfs = np.ascontiguousarray(tfs, dtype=np.uint32) if tfs is not None else None
+    _check(load_library().bm25x_check_vectors(len(off) - 1, _p(off, C.c_uint32), _p(terms, C.c_uint32), _p(tfs, C.c_uint32)))
 
 
 def device_count() -> int:

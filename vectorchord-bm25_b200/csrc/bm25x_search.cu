@@ -744,6 +744,33 @@ extern "C" int bm25x_search_batch_growing(bm25x_index *sealed, bm25x_index *grow
 // ---------------------------------------------------------------------------------------------
 uint32_t bm25x_fieldnorm_to_length(uint8_t fn);
 
+// Invariants of the reference's vector types (crates/bm25/src/vector.rs:46-134): a Document / Query holds strictly
+// ascending keys, a Document's term frequencies are non-zero (`Document::new` / `Query::new` → expect("invalid data")).
+// Host only; bm25x_evaluate_batch applies it to both sides of every pair (its kernel merges the two sorted lists).
+extern "C" int bm25x_check_vectors(uint32_t n, const uint32_t *off, const uint32_t *terms, const uint32_t *tfs) {
+    if (n && (!off || (!terms && off[n] != 0))) {
+        bm25x_set_error("bm25x_check_vectors: null argument");
+        return BM25X_ERR_INVALID;
+    }
+    for (uint32_t i = 0; i < n; ++i) {
+        if (off[i + 1] < off[i]) {
+            bm25x_set_error("invalid data: offsets not monotone at vector %u", i);
+            return BM25X_ERR_INVALID;
+        }
+        for (uint32_t j = off[i]; j < off[i + 1]; ++j) {
+            if (j > off[i] && terms[j] <= terms[j - 1]) {
+                bm25x_set_error("invalid data: keys of vector %u are not strictly ascending", i);
+                return BM25X_ERR_INVALID;
+            }
+            if (tfs && tfs[j] == 0) {
+                bm25x_set_error("invalid data: zero term frequency in vector %u", i);
+                return BM25X_ERR_INVALID;
+            }
+        }
+    }
+    return BM25X_OK;
+}
+
 extern "C" int bm25x_evaluate_batch(bm25x_index *ix, uint32_t n_pairs, const uint32_t *d_off, const uint32_t *d_terms,
                                     const uint32_t *d_tfs, const uint32_t *q_off, const uint32_t *q_terms, double *out) {
     if (!ix || (n_pairs && (!d_off || !q_off || !out))) {
@@ -751,6 +778,15 @@ extern "C" int bm25x_evaluate_batch(bm25x_index *ix, uint32_t n_pairs, const uin
         return BM25X_ERR_INVALID;
     }
     if (n_pairs == 0) return BM25X_OK;
+    if (d_off[n_pairs] != 0 && !d_tfs) {
+        bm25x_set_error("bm25x_evaluate_batch: null argument");
+        return BM25X_ERR_INVALID;
+    }
+    {   // Document / Query invariants (vector.rs:46-134)
+        int vrc = bm25x_check_vectors(n_pairs, d_off, d_terms, d_tfs);
+        if (vrc == BM25X_OK) vrc = bm25x_check_vectors(n_pairs, q_off, q_terms, nullptr);
+        if (vrc != BM25X_OK) return vrc;
+    }
     if (ix->h_df.size() != ix->d.n_terms) {
         bm25x_set_error("bm25x_evaluate_batch: replica not finalized (bm25x_index_finalize_replica)");
         return BM25X_ERR_INVALID;
